@@ -1,0 +1,869 @@
+// bz3_api.cu -- the C ABI of the B200 block codec (include/libbz3.h, include/bz3_b200.h).
+//
+// Host-side orchestration only: every byte of block data is transformed by the CUDA kernels in the
+// headers included below.  Stage order, header layout, validation order and error numbers restate
+// bz3_encode_block / bz3_decode_block (reference src/libbz3.c:585-809); the batch entry points restate
+// bz3_encode_blocks / bz3_decode_blocks (:813-872) with one host thread + one CUDA stream per block.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "../../include/bz3_b200.h"
+#include "common.cuh"
+#include "scan.cuh"
+#include "radix_sort.cuh"
+#include "crc.cuh"
+#include "mrle.cuh"
+#include "lzp.cuh"
+#include "sufsort.cuh"
+#include "unbwt.cuh"
+#include "cm.cuh"
+
+using namespace bz3;
+
+#ifndef BZ3_VERSION_STRING
+#define BZ3_VERSION_STRING "1.5.2-b200"
+#endif
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) & ~(kAlign - 1); }
+
+struct Arena {
+    u8* base = nullptr;
+    size_t size = 0, used = 0;
+    void reset() { used = 0; }
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T));
+        if (used + bytes > size) return nullptr;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return p;
+    }
+};
+
+struct StageClock {
+    cudaEvent_t a[BZ3_STAGE_COUNT], b[BZ3_STAGE_COUNT];
+    bool used[BZ3_STAGE_COUNT];
+};
+
+}  // namespace
+
+struct bz3_state {
+    s32 block_size;
+    s8 last_error;
+    int device;
+    cudaStream_t stream;
+    size_t cap;         // capacity of each data buffer
+    u8* d_buf[3];       // ping-pong buffers + payload buffer
+    s32* d_lut;         // LZP table
+    u32* d_scal;        // device scalars
+    u32* h_scal;        // pinned mirror (1024 u32)
+    Arena arena;        // stage workspace
+    size_t device_bytes;
+    // data staged by bz3_b200_upload / produced by *_resident
+    int resident_buf;   // index of the buffer holding resident data
+    s32 resident_size;
+    // statistics
+    StageClock clk;
+    double stage_ms[2][BZ3_STAGE_COUNT];
+    u64 launches;
+    u64 sort_records;
+    s32 sort_rounds;
+    double sort_ms;
+    int variant[BZ3_STAGE_COUNT];
+};
+
+namespace {
+
+size_t sufsort_arena_bytes(size_t n) {
+    return align_up(4 * n) + align_up(4 * (n + 1)) + 2 * align_up(8 * n) + 6 * align_up(4 * n) +
+           align_up(4 * sufsort_temp_elems((u32)n)) + 16 * kAlign;
+}
+size_t other_arena_bytes(size_t n) {
+    size_t mr = align_up(4 * (n + 2)) + align_up(12 * scan_temp_elems((u32)n)) + align_up(n) + 8 * kAlign;
+    size_t ub = align_up(4 * (n + 2)) + 5 * align_up(4 * ((n >> 5) + 8)) + align_up(4 * rs_temp_elems<u8>((u32)n)) +
+                align_up(65536 * 4) + 8 * kAlign;
+    return mr > ub ? mr : ub;
+}
+
+bool carve_sufsort(bz3_state* s, u32 n, SufsortBuffers& B) {
+    Arena& A = s->arena;
+    A.reset();
+    B.sa = A.take<u32>(n);
+    B.isa = A.take<u32>((size_t)n + 1);
+    for (int i = 0; i < 2; i++) B.key[i] = A.take<u64>(n);
+    for (int i = 0; i < 2; i++) B.val[i] = A.take<u32>(n);
+    for (int i = 0; i < 2; i++) B.pos[i] = A.take<u32>(n);
+    for (int i = 0; i < 2; i++) B.grp[i] = A.take<u32>(n);
+    B.temp = A.take<u32>(sufsort_temp_elems(n));
+    B.d_count = s->d_scal;
+    B.h_count = s->h_scal;
+    return B.temp != nullptr;
+}
+
+struct Timer {
+    bz3_state* s;
+    int stage;
+    Timer(bz3_state* st, int sg) : s(st), stage(sg) {
+        cudaEventRecord(s->clk.a[stage], s->stream);
+    }
+    ~Timer() {
+        cudaEventRecord(s->clk.b[stage], s->stream);
+        s->clk.used[stage] = true;
+    }
+};
+void clocks_begin(bz3_state* s) {
+    for (int i = 0; i < BZ3_STAGE_COUNT; i++) s->clk.used[i] = false;
+}
+void clocks_collect(bz3_state* s, int decode) {
+    cudaStreamSynchronize(s->stream);
+    for (int i = 0; i < BZ3_STAGE_COUNT; i++)
+        if (s->clk.used[i]) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, s->clk.a[i], s->clk.b[i]) == cudaSuccess) s->stage_ms[decode][i] += ms;
+        }
+}
+
+struct LaunchScope {  // folds this thread's launch count into the state
+    bz3_state* s;
+    u64 before;
+    explicit LaunchScope(bz3_state* st) : s(st), before(launch_counter()) {}
+    ~LaunchScope() { s->launches += launch_counter() - before; }
+};
+
+inline void put32(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); }
+inline u32 get32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+
+#define BZ_TRY_ERR(expr)                                 \
+    do {                                                 \
+        if ((expr) != cudaSuccess) return cudaErrorUnknown; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------- stage drivers
+cudaError_t run_crc(bz3_state* s, const u8* d_in, u32 n, u32* crc_out) {
+    BZ_CUDA_TRY(crc_launch(s->stream, d_in, n, 1u, s->d_scal + 32));
+    BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 32, s->d_scal + 32, 4, cudaMemcpyDeviceToHost, s->stream));
+    BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *crc_out = s->h_scal[32];
+    return cudaSuccess;
+}
+
+cudaError_t run_rle_encode(bz3_state* s, const u8* d_in, u32 n, u8* d_out, s32* out_size) {
+    Arena& A = s->arena;
+    A.reset();
+    MrleScratch S;
+    S.heads = A.take<u32>((size_t)n + 2);
+    S.temp = A.take<u32>(scan_temp_elems(n));
+    S.gain = A.take<int>(256);
+    S.flagged = A.take<u8>(256);
+    S.d_count = s->d_scal;
+    S.h_count = s->h_scal;
+    if (!S.flagged) return cudaErrorMemoryAllocation;
+    return mrle_encode(s->stream, d_in, n, d_out, S, out_size);
+}
+
+cudaError_t run_rle_decode(bz3_state* s, const u8* d_in, u32 maxin, u8* d_out, u32 outlen, int* err) {
+    Arena& A = s->arena;
+    A.reset();
+    MrleDecScratch S;
+    S.state = A.take<u8>((size_t)maxin + 8);
+    S.temp = A.take<u32>(3 * scan_temp_elems(maxin));
+    S.flagged = A.take<u8>(256);
+    S.d_count = s->d_scal;
+    S.h_count = s->h_scal;
+    if (!S.flagged) return cudaErrorMemoryAllocation;
+    return mrle_decode(s->stream, d_in, maxin, d_out, outlen, S, err);
+}
+
+cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* result) {
+    if (n < kLzpMinMatch + 32) { *result = -1; return cudaSuccess; }
+    BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
+    lzp_encode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
+    BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
+    BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *result = (s32)s->h_scal[8];
+    return cudaSuccess;
+}
+
+cudaError_t run_lzp_decode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32 max, s32* result) {
+    if (n < 4) { *result = -1; return cudaSuccess; }
+    BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
+    lzp_decode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
+    BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
+    BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *result = (s32)s->h_scal[8];
+    return cudaSuccess;
+}
+
+cudaError_t run_bwt(bz3_state* s, u8* d_in, u32 n, u8* d_out, s32* idx) {
+    SufsortBuffers B;
+    if (!carve_sufsort(s, n, B)) return cudaErrorMemoryAllocation;
+    BZ_CUDA_TRY(cudaMemsetAsync(d_in + n, 0, 16, s->stream));  // zero padding read by the 7-byte key kernel
+    int rounds = 0;
+    cudaError_t e = suffix_bwt(s->stream, d_in, n, d_out, B, idx, &rounds);
+    s->sort_rounds = rounds;
+    return e;
+}
+
+cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, int* status) {
+    Arena& A = s->arena;
+    A.reset();
+    UnbwtBuffers B;
+    int lg;
+    u32 K;
+    unbwt_geometry(n, &lg, &K);
+    B.psi = A.take<u32>((size_t)n + 2);
+    for (int i = 0; i < 2; i++) B.nxt[i] = A.take<u32>((size_t)K + 2);
+    for (int i = 0; i < 2; i++) B.dist[i] = A.take<u32>((size_t)K + 2);
+    B.len = A.take<u32>((size_t)K + 2);
+    B.hist = A.take<u32>(256);
+    B.start = A.take<u32>(257);
+    B.big = A.take<u32>(65536);
+    B.temp = A.take<u32>(rs_temp_elems<u8>(n));
+    B.d_count = s->d_scal;
+    B.h_count = s->h_scal;
+    if (!B.temp) return cudaErrorMemoryAllocation;
+    return unbwt(s->stream, d_in, n, idx, d_out, B, status);
+}
+
+cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* out_size) {
+    s32* d_res = reinterpret_cast<s32*>(s->d_scal + 12);
+    if (s->variant[BZ3_STAGE_CM] == 1)
+        cm_encode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+    else
+        cm_encode_pipelined_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+    BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
+    BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 12, d_res, 4, cudaMemcpyDeviceToHost, s->stream));
+    BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *out_size = (s32)s->h_scal[12];
+    return cudaSuccess;
+}
+
+cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s32 n) {
+    cm_decode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+    BZ_NOTE_LAUNCH();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------- block encode
+struct EncodeResult {
+    u32 crc;
+    s32 bwt_idx, lzp_size, rle_size, payload;
+    int model;
+    int payload_buf;  // d_buf index holding the payload
+};
+
+// input: `size` bytes in d_buf[in_buf] (size >= 64).  Fills R; returns BZ3 error code.
+int encode_core(bz3_state* s, int in_buf, s32 size, EncodeResult& R) {
+    int cur = in_buf, other = (in_buf + 1) % 3, third = (in_buf + 2) % 3;
+    s32 cur_size = size;
+    R.model = 0;
+    R.lzp_size = R.rle_size = -1;
+    {
+        Timer t(s, BZ3_STAGE_CRC);
+        if (run_crc(s, s->d_buf[cur], (u32)size, &R.crc) != cudaSuccess) return BZ3_ERR_INIT;
+    }
+    {
+        Timer t(s, BZ3_STAGE_RLE);
+        if (run_rle_encode(s, s->d_buf[cur], (u32)cur_size, s->d_buf[other], &R.rle_size) != cudaSuccess) return BZ3_ERR_INIT;
+    }
+    if (R.rle_size < cur_size) {  // src/libbz3.c:610
+        int t = cur; cur = other; other = t;
+        cur_size = R.rle_size;
+        R.model |= 4;
+    }
+    {
+        Timer t(s, BZ3_STAGE_LZP);
+        if (run_lzp_encode(s, s->d_buf[cur], cur_size, s->d_buf[other], &R.lzp_size) != cudaSuccess) return BZ3_ERR_INIT;
+    }
+    if (R.lzp_size > 0 && R.lzp_size < cur_size) {  // :617
+        int t = cur; cur = other; other = t;
+        cur_size = R.lzp_size;
+        R.model |= 2;
+    }
+    {
+        Timer t(s, BZ3_STAGE_BWT);
+        if (run_bwt(s, s->d_buf[cur], (u32)cur_size, s->d_buf[other], &R.bwt_idx) != cudaSuccess) return BZ3_ERR_BWT;
+    }
+    if (R.bwt_idx < 0) return BZ3_ERR_BWT;
+    {
+        Timer t(s, BZ3_STAGE_CM);
+        if (run_cm_encode(s, s->d_buf[other], cur_size, s->d_buf[third], &R.payload) != cudaSuccess) return BZ3_ERR_INIT;
+    }
+    R.payload_buf = third;
+    return BZ3_OK;
+}
+
+int header_bytes(int model) { return 9 + ((model & 2) ? 4 : 0) + ((model & 4) ? 4 : 0); }
+
+void write_header(u8* p, const EncodeResult& R) {  // :641-647
+    put32(p, R.crc);
+    put32(p + 4, (u32)R.bwt_idx);
+    p[8] = (u8)R.model;
+    int at = 9;
+    if (R.model & 2) { put32(p + at, (u32)R.lzp_size); at += 4; }
+    if (R.model & 4) { put32(p + at, (u32)R.rle_size); at += 4; }
+}
+
+// ---------------------------------------------------------------------------------- block decode
+struct DecodeHeader {
+    u32 crc;
+    s32 bwt_idx, lzp_size, rle_size, n, payload;
+    int model, hdr;
+};
+
+// Validation that needs only the first bytes of the block (reference :658-737).  Returns 1 when the
+// block is a raw (<64 byte) block, 0 for a coded block, or a negative error.
+int parse_header(bz3_state* s, const u8* head, size_t head_avail, size_t buffer_size, s32 compressed_size,
+                 s32 orig_size, DecodeHeader& H) {
+    (void)head_avail;
+    const s64 bound = (s64)block_bound((size_t)s->block_size);
+    if (buffer_size < 9 || buffer_size < (size_t)(s64)compressed_size) return BZ3_ERR_DATA_SIZE_TOO_SMALL;
+    H.crc = get32(head);
+    H.bwt_idx = (s32)get32(head + 4);
+    if (compressed_size < 0 || (s64)compressed_size > bound) return BZ3_ERR_MALFORMED_HEADER;
+    if (H.bwt_idx == -1) {
+        if (compressed_size - 8 > 64 || compressed_size < 8) return BZ3_ERR_MALFORMED_HEADER;
+        if ((size_t)(compressed_size - 8) > buffer_size) return BZ3_ERR_DATA_SIZE_TOO_SMALL;
+        return 1;
+    }
+    H.model = (s8)head[8];
+    size_t need = 9 + (size_t)((H.model & 2) * 4) + (size_t)((H.model & 4) * 4);  // sic, :697
+    if (buffer_size < need) return BZ3_ERR_DATA_SIZE_TOO_SMALL;
+    H.lzp_size = H.rle_size = -1;
+    int at = 9;
+    if (H.model & 2) { H.lzp_size = (s32)get32(head + at); at += 4; }
+    if (H.model & 4) { H.rle_size = (s32)get32(head + at); at += 4; }
+    H.hdr = at;
+    H.payload = compressed_size - at;
+    if (((H.model & 2) && (H.lzp_size < 0 || H.lzp_size > bound)) || ((H.model & 4) && (H.rle_size < 0 || H.rle_size > bound)))
+        return BZ3_ERR_MALFORMED_HEADER;
+    if (orig_size < 0 || orig_size > bound) return BZ3_ERR_MALFORMED_HEADER;
+    H.n = (H.model & 2) ? H.lzp_size : (H.model & 4) ? H.rle_size : orig_size;
+    size_t l = H.lzp_size < 0 ? 0 : (size_t)H.lzp_size, r = H.rle_size < 0 ? 0 : (size_t)H.rle_size;
+    if (l > buffer_size || r > buffer_size || (size_t)orig_size > buffer_size) return BZ3_ERR_DATA_SIZE_TOO_SMALL;
+    return 0;
+}
+
+// payload: H.payload bytes at d_buf[pay_buf] + pay_off.  On success *out_buf holds *out_size bytes and
+// *crc_ok tells whether the checksum matched.  Mirrors :739-809; sets nothing on the state.
+int decode_core(bz3_state* s, int pay_buf, size_t pay_off, const DecodeHeader& H, size_t buffer_size, s32 orig_size,
+                int* out_buf, s32* out_size, bool* crc_ok) {
+    int a = (pay_buf + 1) % 3, b = (pay_buf + 2) % 3;
+    const s32 bound = (s32)block_bound((size_t)s->block_size);
+    {
+        Timer t(s, BZ3_STAGE_CM);
+        if (run_cm_decode(s, s->d_buf[pay_buf] + pay_off, H.payload, s->d_buf[a], H.n) != cudaSuccess) return BZ3_ERR_INIT;
+    }
+    if (H.bwt_idx > H.n) return BZ3_ERR_MALFORMED_HEADER;  // :750
+    {
+        Timer t(s, BZ3_STAGE_BWT);
+        int status = 0;
+        if (run_unbwt(s, s->d_buf[a], (u32)H.n, H.bwt_idx, s->d_buf[b], &status) != cudaSuccess) return BZ3_ERR_INIT;
+        if (status < 0) return BZ3_ERR_BWT;
+    }
+    int cur = b, other = a;
+    s32 cur_size = H.n;
+    if (H.model & 2) {
+        Timer t(s, BZ3_STAGE_LZP);
+        s32 r = -1;
+        if (run_lzp_decode(s, s->d_buf[cur], H.lzp_size, s->d_buf[other], bound, &r) != cudaSuccess) return BZ3_ERR_INIT;
+        if (r == -1) return BZ3_ERR_CRC;                                   // :769
+        if ((size_t)r > buffer_size) return BZ3_ERR_DATA_SIZE_TOO_SMALL;    // :776
+        cur_size = r;
+        int t2 = cur; cur = other; other = t2;
+    }
+    if (H.model & 4) {
+        Timer t(s, BZ3_STAGE_RLE);
+        int err = 0;
+        if (run_rle_decode(s, s->d_buf[cur], (u32)cur_size, s->d_buf[other], (u32)orig_size, &err) != cudaSuccess)
+            return BZ3_ERR_INIT;
+        if (err) return BZ3_ERR_CRC;  // :786
+        cur_size = orig_size;
+        int t2 = cur; cur = other; other = t2;
+    }
+    if (cur_size > s->block_size || cur_size < 0) return BZ3_ERR_MALFORMED_HEADER;  // :796
+    {
+        Timer t(s, BZ3_STAGE_CRC);
+        u32 crc = 0;
+        if (run_crc(s, s->d_buf[cur], (u32)cur_size, &crc) != cudaSuccess) return BZ3_ERR_INIT;
+        *crc_ok = crc == H.crc;
+    }
+    *out_buf = cur;
+    *out_size = cur_size;
+    return BZ3_OK;
+}
+
+bool use_device(bz3_state* s) { return cudaSetDevice(s->device) == cudaSuccess; }
+
+}  // namespace
+
+// =================================================================================== public ABI
+extern "C" {
+
+BZIP3_API const char* bz3_version(void) { return BZ3_VERSION_STRING; }
+BZIP3_API int8_t bz3_last_error(struct bz3_state* state) { return state->last_error; }
+BZIP3_API size_t bz3_bound(size_t input_size) { return block_bound(input_size); }
+
+BZIP3_API const char* bz3_strerror(struct bz3_state* state) {  // reference src/libbz3.c:512-533
+    switch (state->last_error) {
+        case BZ3_OK: return "No error";
+        case BZ3_ERR_OUT_OF_BOUNDS: return "Data index out of bounds";
+        case BZ3_ERR_BWT: return "Burrows-Wheeler transform failed";
+        case BZ3_ERR_CRC: return "CRC32 check failed";
+        case BZ3_ERR_MALFORMED_HEADER: return "Malformed header";
+        case BZ3_ERR_TRUNCATED_DATA: return "Truncated data";
+        case BZ3_ERR_DATA_TOO_BIG: return "Too much data";
+        case BZ3_ERR_DATA_SIZE_TOO_SMALL:
+            return "Size of buffer `buffer_size` passed to the block decoder (bz3_decode_block) is too small. See "
+                   "function docs for details.";
+        default: return "Unknown error";
+    }
+}
+
+BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
+    if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return nullptr;  // :536
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        fprintf(stderr, "[bz3_b200] no CUDA device: this library has no CPU path\n");
+        return nullptr;
+    }
+    bz3_state* s = new (std::nothrow) bz3_state();
+    if (!s) return nullptr;
+    memset(s, 0, sizeof(*s));
+    s->block_size = block_size;
+    s->device = dev;
+    s->last_error = BZ3_OK;
+    const size_t n = block_bound((size_t)block_size) + 64;
+    s->cap = align_up(n + 256);
+    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && crc_upload_tables() == cudaSuccess && cm_set_smem_attrs() == cudaSuccess;
+    size_t total = 0;
+    for (int i = 0; i < 3 && ok; i++) {
+        ok = cudaMalloc(&s->d_buf[i], s->cap) == cudaSuccess;
+        total += s->cap;
+    }
+    ok = ok && cudaMalloc(&s->d_lut, sizeof(s32) * kLzpSlots) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_scal, 256 * sizeof(u32)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&s->h_scal, 1024 * sizeof(u32)) == cudaSuccess;
+    if (ok) {
+        size_t a = sufsort_arena_bytes(n), b = other_arena_bytes(n);
+        s->arena.size = a > b ? a : b;
+        ok = cudaMalloc(&s->arena.base, s->arena.size) == cudaSuccess;
+        total += s->arena.size + sizeof(s32) * kLzpSlots;
+    }
+    for (int i = 0; i < BZ3_STAGE_COUNT && ok; i++)
+        ok = cudaEventCreate(&s->clk.a[i]) == cudaSuccess && cudaEventCreate(&s->clk.b[i]) == cudaSuccess;
+    s->device_bytes = total;
+    if (!ok) {
+        fprintf(stderr, "[bz3_b200] bz3_new(%d): device setup failed: %s\n", block_size,
+                cudaGetErrorString(cudaGetLastError()));
+        bz3_free(s);
+        return nullptr;
+    }
+    return s;
+}
+
+BZIP3_API void bz3_free(struct bz3_state* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int i = 0; i < 3; i++)
+        if (s->d_buf[i]) cudaFree(s->d_buf[i]);
+    if (s->d_lut) cudaFree(s->d_lut);
+    if (s->d_scal) cudaFree(s->d_scal);
+    if (s->h_scal) cudaFreeHost(s->h_scal);
+    if (s->arena.base) cudaFree(s->arena.base);
+    for (int i = 0; i < BZ3_STAGE_COUNT; i++) {
+        if (s->clk.a[i]) cudaEventDestroy(s->clk.a[i]);
+        if (s->clk.b[i]) cudaEventDestroy(s->clk.b[i]);
+    }
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+BZIP3_API size_t bz3_min_memory_needed(int32_t block_size) {  // host-equivalent figure of the reference, :999-1022
+    if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return 0;
+    size_t total = 40 /* sizeof(struct bz3_state) in the reference */ + 148992 + 24 /* its cm state */;
+    total += block_bound((size_t)block_size);
+    total += (block_bound((size_t)block_size) + 128) * sizeof(s32);
+    total += (size_t)kLzpSlots * sizeof(s32);
+    return total;
+}
+
+// ------------------------------------------------------------------ resident (device) operation
+BZIP3_API int bz3_b200_upload(struct bz3_state* s, const uint8_t* host, int32_t size) {
+    if (!use_device(s) || size < 0 || (size_t)size > s->cap - 64) return -1;
+    Timer t(s, BZ3_STAGE_H2D);
+    if (cudaMemcpyAsync(s->d_buf[0], host, (size_t)size, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return -1;
+    s->resident_buf = 0;
+    s->resident_size = size;
+    return 0;
+}
+
+BZIP3_API int bz3_b200_download(struct bz3_state* s, uint8_t* host, int32_t size) {
+    if (!use_device(s) || size < 0 || size > s->resident_size) return -1;
+    Timer t(s, BZ3_STAGE_D2H);
+    if (cudaMemcpyAsync(host, s->d_buf[s->resident_buf], (size_t)size, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess)
+        return -1;
+    return cudaStreamSynchronize(s->stream) == cudaSuccess ? 0 : -1;
+}
+
+// Encodes the resident data; the encoded block (header + payload) becomes the resident data.
+BZIP3_API int32_t bz3_b200_encode_resident(struct bz3_state* s, int32_t size) {
+    if (!use_device(s)) { s->last_error = BZ3_ERR_INIT; return -1; }
+    LaunchScope ls(s);
+    if (size > s->block_size) { s->last_error = BZ3_ERR_DATA_TOO_BIG; return -1; }  // :588
+    clocks_begin(s);
+    const int in_buf = s->resident_buf;
+    if (size < 64) {  // raw block, :596-601 (last_error untouched)
+        u32 crc = 0;
+        { Timer t(s, BZ3_STAGE_CRC); if (run_crc(s, s->d_buf[in_buf], (u32)size, &crc) != cudaSuccess) { s->last_error = BZ3_ERR_INIT; return -1; } }
+        int ob = (in_buf + 1) % 3;
+        u8 hdr[8];
+        put32(hdr, crc);
+        put32(hdr + 4, 0xFFFFFFFFu);
+        cudaMemcpyAsync(s->d_buf[ob], hdr, 8, cudaMemcpyHostToDevice, s->stream);
+        cudaMemcpyAsync(s->d_buf[ob] + 8, s->d_buf[in_buf], (size_t)size, cudaMemcpyDeviceToDevice, s->stream);
+        s->resident_buf = ob;
+        s->resident_size = size + 8;
+        clocks_collect(s, 0);
+        return size + 8;
+    }
+    EncodeResult R;
+    int e = encode_core(s, in_buf, size, R);
+    if (e != BZ3_OK) { s->last_error = (s8)e; clocks_collect(s, 0); return -1; }
+    // assemble header in front of the payload: payload buffer has 32 spare bytes? no: copy into a free buffer
+    const int hb = header_bytes(R.model);
+    int ob = (R.payload_buf + 1) % 3;
+    u8 hdr[17];
+    write_header(hdr, R);
+    cudaMemcpyAsync(s->d_buf[ob], hdr, (size_t)hb, cudaMemcpyHostToDevice, s->stream);
+    cudaMemcpyAsync(s->d_buf[ob] + hb, s->d_buf[R.payload_buf], (size_t)R.payload, cudaMemcpyDeviceToDevice, s->stream);
+    s->resident_buf = ob;
+    s->resident_size = R.payload + hb;
+    s->last_error = BZ3_OK;
+    clocks_collect(s, 0);
+    return R.payload + hb;
+}
+
+BZIP3_API int32_t bz3_b200_decode_resident(struct bz3_state* s, int32_t compressed_size, int32_t orig_size) {
+    if (!use_device(s)) { s->last_error = BZ3_ERR_INIT; return -1; }
+    LaunchScope ls(s);
+    clocks_begin(s);
+    const int in_buf = s->resident_buf;
+    const size_t buffer_size = s->cap - 64;
+    u8 head[20];
+    memset(head, 0, sizeof head);
+    size_t hn = compressed_size < 0 ? 0 : ((size_t)compressed_size < sizeof head ? (size_t)compressed_size : sizeof head);
+    if (hn) {
+        cudaMemcpyAsync(head, s->d_buf[in_buf], hn, cudaMemcpyDeviceToHost, s->stream);
+        cudaStreamSynchronize(s->stream);
+    }
+    DecodeHeader H;
+    int k = parse_header(s, head, hn, buffer_size, compressed_size, orig_size, H);
+    if (k < 0) { s->last_error = (s8)k; return -1; }
+    if (k == 1) {
+        const s32 len = compressed_size - 8;
+        int ob = (in_buf + 1) % 3;
+        cudaMemcpyAsync(s->d_buf[ob], s->d_buf[in_buf] + 8, (size_t)len, cudaMemcpyDeviceToDevice, s->stream);
+        u32 crc = 0;
+        if (run_crc(s, s->d_buf[ob], (u32)len, &crc) != cudaSuccess) { s->last_error = BZ3_ERR_INIT; return -1; }
+        s->resident_buf = ob;
+        s->resident_size = len;
+        if (crc != H.crc) { s->last_error = BZ3_ERR_CRC; return -1; }
+        return len;  // last_error untouched, :691
+    }
+    int ob = in_buf;
+    s32 osz = 0;
+    bool crc_ok = false;
+    int e = decode_core(s, in_buf, (size_t)H.hdr, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
+    clocks_collect(s, 1);
+    if (e != BZ3_OK) { s->last_error = (s8)e; return -1; }
+    s->resident_buf = ob;
+    s->resident_size = osz;
+    if (!crc_ok) { s->last_error = BZ3_ERR_CRC; return -1; }
+    s->last_error = BZ3_OK;
+    return osz;
+}
+
+// ------------------------------------------------------------------ reference block API (host buffers)
+BZIP3_API int32_t bz3_encode_block(struct bz3_state* s, uint8_t* buffer, int32_t size) {
+    if (size > s->block_size) { s->last_error = BZ3_ERR_DATA_TOO_BIG; return -1; }
+    if (size < 0 || bz3_b200_upload(s, buffer, size) != 0) { s->last_error = BZ3_ERR_INIT; return -1; }
+    int32_t r = bz3_b200_encode_resident(s, size);
+    if (r < 0) return -1;
+    if (bz3_b200_download(s, buffer, r) != 0) { s->last_error = BZ3_ERR_INIT; return -1; }
+    clocks_collect(s, 0);
+    return r;
+}
+
+BZIP3_API int32_t bz3_decode_block(struct bz3_state* s, uint8_t* buffer, size_t buffer_size, int32_t compressed_size,
+                                   int32_t orig_size) {
+    if (!use_device(s)) { s->last_error = BZ3_ERR_INIT; return -1; }
+    LaunchScope ls(s);
+    clocks_begin(s);
+    DecodeHeader H;
+    // the reference reads header bytes straight from the caller's buffer after the size checks
+    if (buffer_size < 9 || buffer_size < (size_t)(s64)compressed_size) { s->last_error = BZ3_ERR_DATA_SIZE_TOO_SMALL; return -1; }
+    u8 head[20];
+    memset(head, 0, sizeof head);
+    memcpy(head, buffer, buffer_size < sizeof head ? buffer_size : sizeof head);
+    int k = parse_header(s, head, sizeof head, buffer_size, compressed_size, orig_size, H);
+    if (k < 0) { s->last_error = (s8)k; return -1; }
+    if (k == 1) {  // raw block :672-692
+        const s32 len = compressed_size - 8;
+        memmove(buffer, buffer + 8, (size_t)len);
+        u32 crc = 0;
+        if (cudaMemcpyAsync(s->d_buf[0], buffer, (size_t)len, cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+            run_crc(s, s->d_buf[0], (u32)len, &crc) != cudaSuccess) { s->last_error = BZ3_ERR_INIT; return -1; }
+        if (crc != H.crc) { s->last_error = BZ3_ERR_CRC; return -1; }
+        return len;
+    }
+    // stage only the payload
+    const s32 pay = H.payload > 0 ? H.payload : 0;
+    {
+        Timer t(s, BZ3_STAGE_H2D);
+        if (pay && cudaMemcpyAsync(s->d_buf[0], buffer + H.hdr, (size_t)pay, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) {
+            s->last_error = BZ3_ERR_INIT; return -1;
+        }
+    }
+    int ob = 0;
+    s32 osz = 0;
+    bool crc_ok = false;
+    int e = decode_core(s, 0, 0, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
+    if (e != BZ3_OK) { s->last_error = (s8)e; clocks_collect(s, 1); return -1; }
+    s->last_error = BZ3_OK;
+    {
+        Timer t(s, BZ3_STAGE_D2H);
+        if (osz && cudaMemcpyAsync(buffer, s->d_buf[ob], (size_t)osz, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) {
+            s->last_error = BZ3_ERR_INIT; return -1;
+        }
+    }
+    clocks_collect(s, 1);
+    s->resident_buf = ob;
+    s->resident_size = osz;
+    if (!crc_ok) { s->last_error = BZ3_ERR_CRC; return -1; }  // :803 (output already copied back, like the reference)
+    return osz;
+}
+
+// ------------------------------------------------------------------ batch API: one thread + stream per block
+BZIP3_API void bz3_encode_blocks(struct bz3_state* states[], uint8_t* buffers[], int32_t sizes[], int32_t n) {
+    std::vector<std::thread> th;
+    std::vector<int32_t> res((size_t)(n > 0 ? n : 0));
+    for (int32_t i = 0; i < n; i++)
+        th.emplace_back([&, i] { res[(size_t)i] = bz3_encode_block(states[i], buffers[i], sizes[i]); });
+    for (auto& t : th) t.join();
+    for (int32_t i = 0; i < n; i++) sizes[i] = res[(size_t)i];
+}
+
+BZIP3_API void bz3_decode_blocks(struct bz3_state* states[], uint8_t* buffers[], size_t buffer_sizes[], int32_t sizes[],
+                                 int32_t orig_sizes[], int32_t n) {
+    std::vector<std::thread> th;
+    for (int32_t i = 0; i < n; i++)
+        th.emplace_back([&, i] { bz3_decode_block(states[i], buffers[i], buffer_sizes[i], sizes[i], orig_sizes[i]); });
+    for (auto& t : th) t.join();
+}
+
+BZIP3_API void bz3_b200_encode_resident_many(struct bz3_state* states[], int32_t sizes[], int32_t results[], int32_t n) {
+    std::vector<std::thread> th;
+    for (int32_t i = 0; i < n; i++) th.emplace_back([&, i] { results[i] = bz3_b200_encode_resident(states[i], sizes[i]); });
+    for (auto& t : th) t.join();
+}
+BZIP3_API void bz3_b200_decode_resident_many(struct bz3_state* states[], int32_t csizes[], int32_t osizes[],
+                                             int32_t results[], int32_t n) {
+    std::vector<std::thread> th;
+    for (int32_t i = 0; i < n; i++)
+        th.emplace_back([&, i] { results[i] = bz3_b200_decode_resident(states[i], csizes[i], osizes[i]); });
+    for (auto& t : th) t.join();
+}
+
+// ------------------------------------------------------------------ frame API (reference :876-997)
+BZIP3_API int bz3_compress(uint32_t block_size, const uint8_t* in, uint8_t* out, size_t in_size, size_t* out_size) {
+    if (block_size > in_size) block_size = (uint32_t)block_bound(in_size);
+    if (block_size <= 65 * 1024) block_size = 65 * 1024;
+    bz3_state* s = bz3_new((int32_t)block_size);
+    if (!s) return BZ3_ERR_INIT;
+    std::vector<u8> scratch;
+    scratch.resize(block_bound(block_size));
+    const size_t buf_max = *out_size;
+    *out_size = 0;
+    u32 n_blocks = (u32)(in_size / block_size);
+    if (in_size % block_size) n_blocks++;
+    if (buf_max < 13 || buf_max < block_bound(in_size)) { bz3_free(s); return BZ3_ERR_DATA_TOO_BIG; }
+    memcpy(out, "BZ3v1", 5);
+    put32(out + 5, block_size);
+    put32(out + 9, n_blocks);
+    *out_size = 13;
+    size_t in_off = 0;
+    for (u32 i = 0; i < n_blocks; i++) {
+        // like the reference, the last block takes in_size % block_size bytes -- 0 when the input is an exact
+        // multiple of the block size (known reference behaviour; kept for format parity)
+        s32 size = (s32)block_size;
+        if (i == n_blocks - 1) size = (s32)(in_size % block_size);
+        memcpy(scratch.data(), in + in_off, (size_t)size);
+        s32 enc = bz3_encode_block(s, scratch.data(), size);
+        if (bz3_last_error(s) != BZ3_OK) { int e = s->last_error; bz3_free(s); return e; }
+        memcpy(out + *out_size + 8, scratch.data(), (size_t)enc);
+        put32(out + *out_size, (u32)enc);
+        put32(out + *out_size + 4, (u32)size);
+        *out_size += (size_t)enc + 8;
+        in_off += (size_t)size;
+    }
+    bz3_free(s);
+    return BZ3_OK;
+}
+
+BZIP3_API int bz3_decompress(const uint8_t* in, uint8_t* out, size_t in_size, size_t* out_size) {
+    if (in_size < 13) return BZ3_ERR_MALFORMED_HEADER;
+    if (memcmp(in, "BZ3v1", 5) != 0) return BZ3_ERR_MALFORMED_HEADER;
+    u32 block_size = get32(in + 5);
+    u32 n_blocks = get32(in + 9);
+    in_size -= 13;
+    in += 13;
+    bz3_state* s = bz3_new((int32_t)block_size);
+    if (!s) return BZ3_ERR_INIT;
+    const size_t cap = block_bound(block_size);
+    std::vector<u8> scratch(cap);
+    const size_t buf_max = *out_size;
+    *out_size = 0;
+    for (u32 i = 0; i < n_blocks; i++) {
+        if (in_size < 8) { bz3_free(s); return BZ3_ERR_MALFORMED_HEADER; }
+        s32 size = (s32)get32(in);
+        if (size < 0 || (u32)size > block_size) { bz3_free(s); return BZ3_ERR_MALFORMED_HEADER; }
+        if (in_size < (size_t)size + 8) { bz3_free(s); return BZ3_ERR_TRUNCATED_DATA; }
+        s32 orig = (s32)get32(in + 4);
+        if (orig < 0) { bz3_free(s); return BZ3_ERR_MALFORMED_HEADER; }
+        if (buf_max < *out_size + (size_t)orig) { bz3_free(s); return BZ3_ERR_DATA_TOO_BIG; }
+        memcpy(scratch.data(), in + 8, (size_t)size);
+        bz3_decode_block(s, scratch.data(), cap, size, orig);
+        if (bz3_last_error(s) != BZ3_OK) { int e = s->last_error; bz3_free(s); return e; }
+        memcpy(out + *out_size, scratch.data(), (size_t)orig);
+        *out_size += (size_t)orig;
+        in += size + 8;
+        in_size -= (size_t)size + 8;
+    }
+    bz3_free(s);
+    return BZ3_OK;
+}
+
+BZIP3_API int bz3_orig_size_sufficient_for_decode(const uint8_t* block, size_t block_size, int32_t orig_size) {  // :1025-1055
+    if (block_size < 9) return -1;
+    if ((s32)get32(block + 4) == -1) return 1;
+    int model = (s8)block[8];
+    size_t need = 9 + (size_t)((model & 2) * 4) + (size_t)((model & 4) * 4);
+    if (block_size < need) return -1;
+    s32 lzp = -1, rle = -1;
+    size_t at = 9;
+    if (model & 2) { lzp = (s32)get32(block + at); at += 4; }
+    if (model & 4) rle = (s32)get32(block + at);
+    size_t bs = (size_t)orig_size;
+    size_t l = lzp < 0 ? 0 : (size_t)lzp, r = rle < 0 ? 0 : (size_t)rle, o = orig_size < 0 ? 0 : (size_t)orig_size;
+    return (l <= bs) && (r <= bs) && (o <= bs);
+}
+
+// ------------------------------------------------------------------ introspection / statistics
+BZIP3_API int bz3_b200_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+BZIP3_API int bz3_b200_state_device(struct bz3_state* s) { return s->device; }
+BZIP3_API size_t bz3_b200_device_bytes(struct bz3_state* s) { return s->device_bytes; }
+BZIP3_API void bz3_b200_stats_reset(struct bz3_state* s) {
+    memset(s->stage_ms, 0, sizeof s->stage_ms);
+    s->launches = 0;
+}
+BZIP3_API double bz3_b200_stage_ms(struct bz3_state* s, int stage, int decode) {
+    if (stage < 0 || stage >= BZ3_STAGE_COUNT) return 0.0;
+    return s->stage_ms[decode ? 1 : 0][stage];
+}
+BZIP3_API uint64_t bz3_b200_kernel_launches(struct bz3_state* s) { return s->launches; }
+BZIP3_API void bz3_b200_last_sort_stats(struct bz3_state* s, uint64_t* records, int32_t* rounds, double* ms) {
+    if (records) *records = s->sort_records;
+    if (rounds) *rounds = s->sort_rounds;
+    if (ms) *ms = s->sort_ms;
+}
+BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant) {
+    if (stage >= 0 && stage < BZ3_STAGE_COUNT) s->variant[stage] = variant;
+}
+
+// ------------------------------------------------------------------ single stages on host buffers (tests)
+namespace {
+bool stage_in(bz3_state* s, const u8* in, size_t n, int buf) {
+    if (!use_device(s) || n > s->cap - 64) return false;
+    return cudaMemcpyAsync(s->d_buf[buf], in, n, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+}
+bool stage_out(bz3_state* s, u8* out, size_t n, int buf) {
+    if (n && cudaMemcpyAsync(out, s->d_buf[buf], n, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return false;
+    return cudaStreamSynchronize(s->stream) == cudaSuccess;
+}
+}  // namespace
+
+BZIP3_API uint32_t bz3_b200_stage_crc(struct bz3_state* s, const uint8_t* in, int32_t n) {
+    u32 crc = 0;
+    if (!stage_in(s, in, (size_t)n, 0) || run_crc(s, s->d_buf[0], (u32)n, &crc) != cudaSuccess) return 0xDEADBEEF;
+    return crc;
+}
+BZIP3_API int32_t bz3_b200_stage_rle_encode(struct bz3_state* s, const uint8_t* in, int32_t n, uint8_t* out) {
+    s32 r = -1;
+    if (!stage_in(s, in, (size_t)n, 0) || run_rle_encode(s, s->d_buf[0], (u32)n, s->d_buf[1], &r) != cudaSuccess) return -100;
+    if (r >= 0 && (size_t)r <= s->cap && !stage_out(s, out, (size_t)r, 1)) return -100;
+    return r;
+}
+BZIP3_API int bz3_b200_stage_rle_decode(struct bz3_state* s, const uint8_t* in, int32_t maxin, uint8_t* out, int32_t outlen) {
+    int err = 1;
+    cudaMemsetAsync(s->d_buf[1], 0, (size_t)outlen, s->stream);
+    if (!stage_in(s, in, (size_t)maxin, 0) || run_rle_decode(s, s->d_buf[0], (u32)maxin, s->d_buf[1], (u32)outlen, &err) != cudaSuccess)
+        return -100;
+    if (!stage_out(s, out, (size_t)outlen, 1)) return -100;
+    return err;
+}
+BZIP3_API int32_t bz3_b200_stage_lzp_encode(struct bz3_state* s, const uint8_t* in, int32_t n, uint8_t* out) {
+    s32 r = -1;
+    if (!stage_in(s, in, (size_t)n, 0) || run_lzp_encode(s, s->d_buf[0], n, s->d_buf[1], &r) != cudaSuccess) return -100;
+    if (r > 0 && !stage_out(s, out, (size_t)r, 1)) return -100;
+    return r;
+}
+BZIP3_API int32_t bz3_b200_stage_lzp_decode(struct bz3_state* s, const uint8_t* in, int32_t n, uint8_t* out, int32_t max) {
+    s32 r = -1;
+    if ((size_t)max > s->cap - 64) return -100;
+    if (!stage_in(s, in, (size_t)n, 0) || run_lzp_decode(s, s->d_buf[0], n, s->d_buf[1], max, &r) != cudaSuccess) return -100;
+    if (r > 0 && !stage_out(s, out, (size_t)r, 1)) return -100;
+    return r;
+}
+BZIP3_API int32_t bz3_b200_stage_bwt(struct bz3_state* s, const uint8_t* in, int32_t n, uint8_t* out) {
+    s32 idx = -1;
+    LaunchScope ls(s);
+    if (!stage_in(s, in, (size_t)n, 0) || run_bwt(s, s->d_buf[0], (u32)n, s->d_buf[1], &idx) != cudaSuccess) return -100;
+    if (!stage_out(s, out, (size_t)n, 1)) return -100;
+    return idx;
+}
+BZIP3_API int32_t bz3_b200_stage_unbwt(struct bz3_state* s, const uint8_t* in, int32_t n, int32_t idx, uint8_t* out) {
+    int status = 0;
+    if (!stage_in(s, in, (size_t)n, 0) || run_unbwt(s, s->d_buf[0], (u32)n, idx, s->d_buf[1], &status) != cudaSuccess) return -100;
+    if (status == 0 && !stage_out(s, out, (size_t)n, 1)) return -100;
+    return status;
+}
+BZIP3_API int32_t bz3_b200_stage_cm_encode(struct bz3_state* s, const uint8_t* in, int32_t n, uint8_t* out) {
+    s32 r = -1;
+    if (!stage_in(s, in, (size_t)n, 0) || run_cm_encode(s, s->d_buf[0], n, s->d_buf[1], &r) != cudaSuccess) return -100;
+    if (r > 0 && !stage_out(s, out, (size_t)r, 1)) return -100;
+    return r;
+}
+BZIP3_API int bz3_b200_stage_cm_decode(struct bz3_state* s, const uint8_t* in, int32_t insize, uint8_t* out, int32_t n) {
+    if (!stage_in(s, in, (size_t)(insize > 0 ? insize : 0), 0) || run_cm_decode(s, s->d_buf[0], insize, s->d_buf[1], n) != cudaSuccess)
+        return -100;
+    return stage_out(s, out, (size_t)n, 1) ? 0 : -100;
+}
+
+}  // extern "C"

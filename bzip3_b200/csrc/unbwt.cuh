@@ -1,0 +1,234 @@
+// unbwt.cuh -- inverse BWT on the GPU.
+//
+// Replaces libsais_unbwt (reference include/libsais.h:5260, called from src/libbz3.c:758), whose
+// decoder is one n/2-step dependent pointer chase.  Here:
+//   1. byte histogram of L                                        (n read)
+//   2. psi = stable counting sort of the row numbers by L         (one radix pass: n read, 4n written)
+//      psi maps the row of suffix T[k..] to the row of T[k+1..]; rows 0..n, row `idx` owns no byte.
+//   3. every s-th row plus row idx is a walker start; each walks psi until the next start row
+//      (all walkers in flight at once: the chase is latency-hidden by ~10^6 independent chains)
+//   4. pointer-jumping list ranking over the ~n/s starts gives each walker its text offset
+//   5. second walk writes the text; first-column bytes come from a binary search over the 257 bucket
+//      starts in shared memory, so each step costs one random 4-byte HBM access.
+// For a corrupt stream the psi graph is a path idx -> ... -> row 0 plus stray cycles; what the
+// reference emits after the path ends is reproduced (see oracle/bz3_oracle.c:orc_unbwt for the
+// derivation) so that the CRC verdict of the block decoder matches on hostile input.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+#include "radix_sort.cuh"
+
+namespace bz3 {
+
+__global__ void __launch_bounds__(256) hist256_kernel(const u8* __restrict__ in, u32 n, u32* __restrict__ hist) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&h[in[i]], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// start[c] = 1 + number of bytes smaller than c;  start[256] = n + 1
+__global__ void unbwt_starts_kernel(const u32* __restrict__ hist, u32* __restrict__ start) {
+    __shared__ u32 s[257];
+    if (threadIdx.x == 0) {
+        u32 acc = 1;
+        for (int c = 0; c < 256; c++) { s[c] = acc; acc += hist[c]; }
+        s[256] = acc;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 257; c += blockDim.x) start[c] = s[c];
+}
+
+struct ValRowOfL {  // row number of the j-th byte of L
+    u32 idx;
+    BZ_D u32 operator()(u32 j) const { return j < idx ? j : j + 1; }
+};
+
+BZ_D u32 first_column(const u32* sstart, u32 q) {  // largest c with start[c] <= q  (q >= 1)
+    u32 lo = 0, hi = 256;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        u32 mid = (lo + hi) >> 1;
+        if (sstart[mid] <= q) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// entries 0..K-1 are rows k*s, entry K is row idx.  Entry 0 (row 0) is the terminal.
+__global__ void __launch_bounds__(256) unbwt_walk1_kernel(const u32* __restrict__ psi, u32 K, u32 s_mask, int s_log2,
+                                                          u32 idx, u32* __restrict__ nxt, u32* __restrict__ len) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > K) return;
+    if (k == 0) { nxt[0] = 0; len[0] = 0; return; }
+    u32 q = (k < K) ? (k << s_log2) : idx;
+    u32 steps = 0;
+    do {
+        q = psi[q];
+        steps++;
+    } while (q & s_mask);
+    nxt[k] = q >> s_log2;
+    len[k] = steps;
+}
+
+__global__ void __launch_bounds__(256) unbwt_jump_kernel(const u32* __restrict__ nxt, const u32* __restrict__ dist,
+                                                         u32 count, u32* __restrict__ nxt2, u32* __restrict__ dist2) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    u32 t = nxt[k];
+    u32 d = dist[k] + dist[t];
+    if (d > 0x7FFFFFFFu) d = 0x7FFFFFFFu;
+    nxt2[k] = nxt[t];
+    dist2[k] = d;
+}
+
+__global__ void __launch_bounds__(256)
+unbwt_walk2_kernel(const u32* __restrict__ psi, const u32* __restrict__ start, u32 K, int s_log2, u32 idx,
+                   const u32* __restrict__ nxt_final, const u32* __restrict__ dist_final, const u32* __restrict__ len,
+                   u32 limit, u8* __restrict__ out) {
+    __shared__ u32 sstart[257];
+    for (int c = threadIdx.x; c < 257; c += blockDim.x) sstart[c] = start[c];
+    __syncthreads();
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > K || k == 0) return;
+    if (nxt_final[k] != 0) return;  // on a stray cycle: not part of the text
+    const u32 m = dist_final[K];
+    u32 off = m - dist_final[k];
+    u32 q = (k < K) ? (k << s_log2) : idx;
+    const u32 steps = len[k];
+    for (u32 j = 0; j < steps; j++) {
+        u32 at = off + j;
+        if (at < limit) out[at] = (u8)first_column(sstart, q);
+        q = psi[q];
+    }
+}
+
+// ---- reproduction of the reference's behaviour after an early end of the path (corrupt input only)
+__global__ void __launch_bounds__(256) unbwt_bigram_kernel(const u32* __restrict__ psi, const u32* __restrict__ start,
+                                                           u32 n, u32 qstar, u32* __restrict__ big) {
+    __shared__ u32 sstart[257];
+    for (int c = threadIdx.x; c < 257; c += blockDim.x) sstart[c] = start[c];
+    __syncthreads();
+    for (u32 q = 1 + blockIdx.x * blockDim.x + threadIdx.x; q <= n; q += gridDim.x * blockDim.x) {
+        if (q == qstar) continue;
+        u32 w = (first_column(sstart, q) << 8) | first_column(sstart, psi[q]);
+        atomicAdd(&big[w], 1u);
+    }
+}
+// res[0] = smallest bigram present, res[1] = bigram the reference reads when a pair starts on q*
+__global__ void unbwt_filler_words_kernel(const u32* __restrict__ big, u32 n, u32 lastc, u32 qstar, u32* res) {
+    if (threadIdx.x || blockIdx.x) return;
+    int shift = 0;
+    while ((n >> shift) > (1u << 17)) shift++;
+    u32 wmin = 65536, hint = 65536, sum = 1;
+    for (u32 w = 0; w < 65536; w++) {
+        u32 c = big[w];
+        if ((w & 255u) == 0 && (w >> 8) == lastc) sum += 1;
+        sum += c;
+        if (c) {
+            if (wmin == 65536) wmin = w;
+            if (hint == 65536 && ((sum - 1) >> shift) >= (qstar >> shift)) hint = w;
+        }
+    }
+    u32 wstar = hint == 65536 ? 0 : hint;  // unassigned accelerator slots read as zero
+    // advance to the first bucket whose end exceeds q*
+    sum = 1;
+    u32 endw = 0;
+    for (u32 w = 0; w < 65536; w++) {
+        if ((w & 255u) == 0 && (w >> 8) == lastc) sum += 1;
+        sum += big[w];
+        if (w >= wstar && sum > qstar) { endw = w; break; }
+        if (w == 65535) endw = 65536;
+    }
+    res[0] = wmin & 0xFFFFu;
+    res[1] = endw & 0xFFFFu;
+}
+__global__ void __launch_bounds__(256) unbwt_fill_kernel(u8* out, u32 n, u32 m, const u32* res) {
+    u32 pair = blockIdx.x * blockDim.x + threadIdx.x;  // pair p covers bytes 2p, 2p+1
+    if (pair >= (n >> 1)) return;
+    u32 w;
+    if ((m & 1u) && pair == (m - 1) / 2) w = res[1];
+    else if (2 * pair >= m + (m & 1u)) w = res[0];
+    else return;
+    out[2 * pair] = (u8)(w >> 8);
+    out[2 * pair + 1] = (u8)w;
+}
+__global__ void unbwt_last_byte_kernel(const u8* L, u8* out, u32 n) { out[n - 1] = L[0]; }
+
+struct UnbwtBuffers {
+    u32* psi;       // [n+2]
+    u32* nxt[2];    // [K+2] each
+    u32* dist[2];   // [K+2] each
+    u32* len;       // [K+2]
+    u32* hist;      // [256]
+    u32* start;     // [257]
+    u32* big;       // [65536]
+    u32* temp;      // radix scratch rs_temp_elems<u8>(n)
+    u32* d_count;
+    u32* h_count;
+};
+
+inline void unbwt_geometry(u32 n, int* s_log2, u32* K) {
+    int lg = 5;  // spacing >= 32
+    while (((u64)n >> lg) > (1u << 20)) lg++;
+    *s_log2 = lg;
+    *K = (n >> lg) + 1;  // rows 0, s, 2s, ... <= n
+}
+
+// L: n bytes (device), out: n bytes (device).  Returns 0 or -1 in *status (argument validation of
+// include/libsais.h:5210-5232).
+inline cudaError_t unbwt(cudaStream_t st, const u8* L, u32 n, s32 idx, u8* out, const UnbwtBuffers& B, int* status) {
+    *status = 0;
+    if (n <= 1) {
+        if (idx != (s32)n) { *status = -1; return cudaSuccess; }
+        if (n == 1) BZ_CUDA_TRY(cudaMemcpyAsync(out, L, 1, cudaMemcpyDeviceToDevice, st));
+        return cudaSuccess;
+    }
+    if (idx <= 0 || idx > (s32)n) { *status = -1; return cudaSuccess; }
+    BZ_CUDA_TRY(cudaMemsetAsync(B.hist, 0, 256 * sizeof(u32), st));
+    u32 hb = (n + 256 * 64 - 1) / (256 * 64);
+    if (hb > 148 * 8) hb = 148 * 8;
+    hist256_kernel<<<hb, 256, 0, st>>>(L, n, B.hist); BZ_NOTE_LAUNCH();
+    unbwt_starts_kernel<<<1, 256, 0, st>>>(B.hist, B.start); BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
+    BZ_CUDA_TRY(cudaMemsetAsync(B.psi, 0, sizeof(u32), st));
+    BZ_CUDA_TRY((rs_pass<u8, false, true, ValRowOfL>(st, L, ValRowOfL{(u32)idx}, (u8*)nullptr, B.psi + 1, n, 0, 8, B.temp)));
+    int lg;
+    u32 K;
+    unbwt_geometry(n, &lg, &K);
+    const u32 cnt = K + 1;
+    unbwt_walk1_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(B.psi, K, (1u << lg) - 1u, lg, (u32)idx, B.nxt[0], B.len); BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
+    BZ_CUDA_TRY(cudaMemcpyAsync(B.dist[0], B.len, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    int cur = 0;
+    for (u32 span = 1; span < cnt; span <<= 1) {
+        unbwt_jump_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(B.nxt[cur], B.dist[cur], cnt, B.nxt[cur ^ 1], B.dist[cur ^ 1]); BZ_NOTE_LAUNCH();
+        cur ^= 1;
+    }
+    BZ_CUDA_TRY(cudaGetLastError());
+    const u32 limit = 2 * (n >> 1);
+    unbwt_walk2_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(B.psi, B.start, K, lg, (u32)idx, B.nxt[cur], B.dist[cur], B.len,
+                                                          limit, out); BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
+    // path length: n for a valid transform
+    BZ_CUDA_TRY(cudaMemcpyAsync(B.h_count, B.dist[cur] + K, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    BZ_CUDA_TRY(cudaMemcpyAsync(B.h_count + 1, B.start, 257 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    BZ_CUDA_TRY(cudaMemcpyAsync(B.h_count + 300, L, 1, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA_TRY(cudaStreamSynchronize(st));
+    const u32 m = B.h_count[0];
+    if (m < n) {
+        const u32 lastc = *reinterpret_cast<const u8*>(B.h_count + 300);
+        const u32 qstar = B.h_count[1 + lastc];
+        BZ_CUDA_TRY(cudaMemsetAsync(B.big, 0, 65536 * sizeof(u32), st));
+        unbwt_bigram_kernel<<<148 * 4, 256, 0, st>>>(B.psi, B.start, n, qstar, B.big); BZ_NOTE_LAUNCH();
+        unbwt_filler_words_kernel<<<1, 1, 0, st>>>(B.big, n, lastc, qstar, B.d_count); BZ_NOTE_LAUNCH();
+        unbwt_fill_kernel<<<((n >> 1) + 255) / 256, 256, 0, st>>>(out, n, m, B.d_count); BZ_NOTE_LAUNCH();
+        BZ_CUDA_TRY(cudaGetLastError());
+    }
+    unbwt_last_byte_kernel<<<1, 1, 0, st>>>(L, out, n); BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
+    return cudaSuccess;
+}
+
+}  // namespace bz3

@@ -1,0 +1,68 @@
+/*
+ * bz3_b200.h -- extensions of the B200 block codec beyond the reference ABI (libbz3.h).
+ * Plain C types only.  None of these exist in the reference; they expose
+ *   - device-resident operation (input uploaded once, codec timed without PCIe traffic),
+ *   - per-stage device timings (CUDA events on the state's stream),
+ *   - single-stage entry points used by the parity tests.
+ */
+#ifndef BZ3_B200_H
+#define BZ3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "libbz3.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* stage indices for bz3_b200_stage_ms() */
+enum {
+    BZ3_STAGE_H2D = 0, BZ3_STAGE_CRC, BZ3_STAGE_RLE, BZ3_STAGE_LZP, BZ3_STAGE_BWT, BZ3_STAGE_CM, BZ3_STAGE_D2H,
+    BZ3_STAGE_COUNT
+};
+
+/* number of CUDA devices visible / device a state lives on */
+BZIP3_API int bz3_b200_device_count(void);
+BZIP3_API int bz3_b200_state_device(struct bz3_state *state);
+BZIP3_API size_t bz3_b200_device_bytes(struct bz3_state *state);
+
+/* Device-resident codec: stage `size` bytes into the state, run the block codec without host copies,
+ * fetch the result.  encode_resident/decode_resident return what bz3_encode_block/bz3_decode_block
+ * would return and set last_error the same way. */
+BZIP3_API int bz3_b200_upload(struct bz3_state *state, const uint8_t *host, int32_t size);
+BZIP3_API int32_t bz3_b200_encode_resident(struct bz3_state *state, int32_t size);
+BZIP3_API int32_t bz3_b200_decode_resident(struct bz3_state *state, int32_t compressed_size, int32_t orig_size);
+BZIP3_API int bz3_b200_download(struct bz3_state *state, uint8_t *host, int32_t size);
+/* n states at once (one host thread per state); results[i] receives the per-block return value */
+BZIP3_API void bz3_b200_encode_resident_many(struct bz3_state *states[], int32_t sizes[], int32_t results[], int32_t n);
+BZIP3_API void bz3_b200_decode_resident_many(struct bz3_state *states[], int32_t csizes[], int32_t osizes[],
+                                             int32_t results[], int32_t n);
+
+/* accumulated device milliseconds per stage since the last reset; launches = kernels launched */
+BZIP3_API void bz3_b200_stats_reset(struct bz3_state *state);
+BZIP3_API double bz3_b200_stage_ms(struct bz3_state *state, int stage, int decode);
+BZIP3_API uint64_t bz3_b200_kernel_launches(struct bz3_state *state);
+/* details of the last suffix sort: records sorted over all radix passes, rounds, device ms in passes */
+BZIP3_API void bz3_b200_last_sort_stats(struct bz3_state *state, uint64_t *records, int32_t *rounds, double *ms);
+
+/* single stages on HOST buffers (parity tests).  Each returns the stage's own return value. */
+BZIP3_API uint32_t bz3_b200_stage_crc(struct bz3_state *state, const uint8_t *in, int32_t n);
+BZIP3_API int32_t bz3_b200_stage_rle_encode(struct bz3_state *state, const uint8_t *in, int32_t n, uint8_t *out);
+BZIP3_API int bz3_b200_stage_rle_decode(struct bz3_state *state, const uint8_t *in, int32_t maxin, uint8_t *out,
+                                        int32_t outlen);
+BZIP3_API int32_t bz3_b200_stage_lzp_encode(struct bz3_state *state, const uint8_t *in, int32_t n, uint8_t *out);
+BZIP3_API int32_t bz3_b200_stage_lzp_decode(struct bz3_state *state, const uint8_t *in, int32_t n, uint8_t *out,
+                                            int32_t max);
+BZIP3_API int32_t bz3_b200_stage_bwt(struct bz3_state *state, const uint8_t *in, int32_t n, uint8_t *out);
+BZIP3_API int32_t bz3_b200_stage_unbwt(struct bz3_state *state, const uint8_t *in, int32_t n, int32_t idx, uint8_t *out);
+BZIP3_API int32_t bz3_b200_stage_cm_encode(struct bz3_state *state, const uint8_t *in, int32_t n, uint8_t *out);
+BZIP3_API int bz3_b200_stage_cm_decode(struct bz3_state *state, const uint8_t *in, int32_t insize, uint8_t *out,
+                                       int32_t n);
+/* implementation selectors for stages that have more than one kernel form (0 = default/fastest) */
+BZIP3_API void bz3_b200_set_variant(struct bz3_state *state, int stage, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
