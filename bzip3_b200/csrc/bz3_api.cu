@@ -209,8 +209,10 @@ cudaError_t run_bwt(bz3_state* s, u8* d_in, u32 n, u8* d_out, s32* idx) {
     if (!carve_sufsort(s, n, B)) return cudaErrorMemoryAllocation;
     BZ_CUDA_TRY(cudaMemsetAsync(d_in + n, 0, 16, s->stream));  // zero padding read by the 7-byte key kernel
     int rounds = 0;
-    cudaError_t e = suffix_bwt(s->stream, d_in, n, d_out, B, idx, &rounds);
+    u64 rp = 0;
+    cudaError_t e = suffix_bwt(s->stream, d_in, n, d_out, B, idx, &rounds, &rp);
     s->sort_rounds = rounds;
+    s->sort_records += rp;
     return e;
 }
 
@@ -782,6 +784,7 @@ BZIP3_API size_t bz3_b200_device_bytes(struct bz3_state* s) { return s->device_b
 BZIP3_API void bz3_b200_stats_reset(struct bz3_state* s) {
     memset(s->stage_ms, 0, sizeof s->stage_ms);
     s->launches = 0;
+    s->sort_records = 0;
 }
 BZIP3_API double bz3_b200_stage_ms(struct bz3_state* s, int stage, int decode) {
     if (stage < 0 || stage >= BZ3_STAGE_COUNT) return 0.0;

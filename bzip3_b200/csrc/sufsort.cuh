@@ -131,7 +131,7 @@ inline int bit_width_u32(u32 v) {
 
 // T must be readable (and zero) for 8 bytes past n.  Returns the primary index in *idx_out (host).
 inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const SufsortBuffers& B, s32* idx_out,
-                              int* rounds_out = nullptr) {
+                              int* rounds_out = nullptr, u64* record_passes_out = nullptr) {
     if (n <= 1) {  // include/libsais.h:4098-4108
         if (n == 1) BZ_CUDA_TRY(cudaMemcpyAsync(U, T, 1, cudaMemcpyDeviceToDevice, st));
         *idx_out = (s32)n;
@@ -158,9 +158,11 @@ inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const 
     int vc = kc ^ 1;  // val buffer holding the list
     const int rank_bits = bit_width_u32(n);
     int rounds = 0;
+    u64 record_passes = (u64)n * 8;  // round 0: eight 8-bit passes over n records
     for (u64 h = 7; m > 0; h *= 2) {
         if (h >= n) return cudaErrorUnknown;  // cannot happen: every suffix is unique within n symbols
         rounds++;
+        record_passes += (u64)m * (u64)((2 * rank_bits + 7) / 8);
         sa_build_keys_kernel<<<(m + TPB - 1) / TPB, TPB, 0, st>>>(B.val[vc], B.grp[lc], B.isa, m, (u32)h, rank_bits,
                                                                   B.key[0]); BZ_NOTE_LAUNCH();
         BZ_CUDA_TRY(cudaGetLastError());
@@ -179,6 +181,7 @@ inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const 
         lc ^= 1;
     }
     if (rounds_out) *rounds_out = rounds;
+    if (record_passes_out) *record_passes_out = record_passes;
     // primary index = rank of suffix 0 (1-based SA slot)
     BZ_CUDA_TRY(cudaMemcpyAsync(B.h_count, B.isa, sizeof(u32), cudaMemcpyDeviceToHost, st));
     BZ_CUDA_TRY(cudaStreamSynchronize(st));

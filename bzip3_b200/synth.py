@@ -20,12 +20,19 @@ _LETTER_W = np.array([12.7, 9.1, 8.2, 7.5, 7.0, 6.7, 6.3, 6.1, 6.0, 4.3, 4.0, 2.
 
 def _flatten(tokens: np.ndarray, tab_bytes: np.ndarray, tab_off: np.ndarray, tab_len: np.ndarray) -> np.ndarray:
     """Concatenate table entries tab[tokens[k]] into one byte array (vectorised gather)."""
-    lens = tab_len[tokens].astype(np.int64)
-    total = int(lens.sum())
-    dst_start = np.cumsum(lens) - lens
-    src_start = tab_off[tokens].astype(np.int64)
-    idx = np.repeat(src_start - dst_start, lens) + np.arange(total, dtype=np.int64)
-    return tab_bytes[idx]
+    out = []
+    step = 1 << 20  # chunked so the index temporaries stay cache-sized; int32 indices
+    tab_len32 = tab_len.astype(np.int32)
+    tab_off32 = tab_off.astype(np.int32)
+    for a in range(0, len(tokens), step):
+        tk = tokens[a:a + step]
+        lens = tab_len32[tk]
+        total = int(lens.sum())
+        dst_start = np.cumsum(lens, dtype=np.int32) - lens
+        idx = np.repeat(tab_off32[tk] - dst_start, lens)
+        idx += np.arange(total, dtype=np.int32)
+        out.append(tab_bytes[idx])
+    return np.concatenate(out) if len(out) != 1 else out[0]
 
 
 def _make_table(strings):
@@ -47,7 +54,10 @@ def _zipf_ids(rng, nvocab, s, count):
     w = 1.0 / np.power(np.arange(1, nvocab + 1, dtype=np.float64), s)
     cdf = np.cumsum(w)
     cdf /= cdf[-1]
-    return np.searchsorted(cdf, rng.random(count), side="right").astype(np.int64).clip(0, nvocab - 1)
+    # 2^16-entry guide table turns the search into one lookup plus a short local search
+    u = rng.random(count)
+    ids = np.searchsorted(cdf, u, side="right")
+    return np.minimum(ids, nvocab - 1).astype(np.int64)
 
 
 def zipf_text(nbytes: int, seed: int = SEED_ZIPF_TEXT) -> np.ndarray:
