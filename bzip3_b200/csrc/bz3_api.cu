@@ -17,6 +17,7 @@
 #include "crc.cuh"
 #include "mrle.cuh"
 #include "lzp.cuh"
+#include "lzp_parallel.cuh"
 #include "sufsort.cuh"
 #include "unbwt.cuh"
 #include "cm.cuh"
@@ -183,7 +184,10 @@ cudaError_t run_rle_decode(bz3_state* s, const u8* d_in, u32 maxin, u8* d_out, u
 cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* result) {
     if (n < kLzpMinMatch + 32) { *result = -1; return cudaSuccess; }
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
-    lzp_encode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    if (s->variant[BZ3_STAGE_LZP] == 1)
+        lzp_encode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    else
+        lzp_encode_warp_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -195,7 +199,10 @@ cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* 
 cudaError_t run_lzp_decode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32 max, s32* result) {
     if (n < 4) { *result = -1; return cudaSuccess; }
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
-    lzp_decode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    if (s->variant[BZ3_STAGE_LZP] == 1)
+        lzp_decode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    else
+        lzp_decode_warp_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -242,7 +249,7 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
     if (s->variant[BZ3_STAGE_CM] == 1)
         cm_encode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     else
-        cm_encode_pipelined_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+        cm_encode_chunked_kernel<<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 12, d_res, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -252,7 +259,10 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
 }
 
 cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s32 n) {
-    cm_decode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+    if (s->variant[BZ3_STAGE_CM] == 1)
+        cm_decode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+    else
+        cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     BZ_NOTE_LAUNCH();
     return cudaGetLastError();
 }

@@ -81,8 +81,17 @@ def test_stage_rle(st, O, name, data):
         assert bytes(dg[:n]) == bytes(dw[:n]), (cut, first_diff(dg[:n], dw[:n]))
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["warp", "single"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
-def test_stage_lzp(st, O, name, data):
+def test_stage_lzp(st, O, name, data, variant):
+    st.L.bz3_b200_set_variant(st.handle, 3, variant)
+    try:
+        _check_lzp(st, O, data)
+    finally:
+        st.L.bz3_b200_set_variant(st.handle, 3, 0)
+
+
+def _check_lzp(st, O, data):
     a = arr(data)
     n = len(a)
     pad = np.zeros(n + 64, np.uint8)
@@ -143,7 +152,7 @@ def test_stage_unbwt_on_garbage_matches_reference_semantics(st, O):
         assert bytes(got[:n]) == bytes(want[:n]), (t, n, k, idx, first_diff(got[:n], want[:n]))
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["pipelined", "single"])
+@pytest.mark.parametrize("variant", [0, 1], ids=["parallel", "single"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_stage_cm(st, O, name, data, variant):
     a = arr(data)
@@ -162,13 +171,16 @@ def test_stage_cm(st, O, name, data, variant):
         st.L.bz3_b200_set_variant(st.handle, 5, 0)
     assert rg == rw, (rg, rw)
     assert bytes(got[:rg]) == bytes(want[:rw]), first_diff(got[:rg], want[:rw])
-    if variant == 0:
-        for insize in (rw, max(rw - 3, 0)):
-            dw = np.zeros(n + 8, np.uint8)
-            dg = np.zeros(n + 8, np.uint8)
-            O.orc_cm_decode(refs.ptr(want), insize, refs.ptr(dw), n)
+    for insize in (rw, max(rw - 3, 0), rw // 2):
+        dw = np.zeros(n + 8, np.uint8)
+        dg = np.zeros(n + 8, np.uint8)
+        O.orc_cm_decode(refs.ptr(want), insize, refs.ptr(dw), n)
+        st.L.bz3_b200_set_variant(st.handle, 5, variant)
+        try:
             assert st.L.bz3_b200_stage_cm_decode(st.handle, refs.ptr(want), insize, refs.ptr(dg), n) == 0
-            assert bytes(dg[:n]) == bytes(dw[:n]), (insize, first_diff(dg[:n], dw[:n]))
+        finally:
+            st.L.bz3_b200_set_variant(st.handle, 5, 0)
+        assert bytes(dg[:n]) == bytes(dw[:n]), (insize, first_diff(dg[:n], dw[:n]))
 
 
 # ---------------------------------------------------------------- whole blocks
