@@ -248,8 +248,12 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
     s32* d_res = reinterpret_cast<s32*>(s->d_scal + 12);
     if (s->variant[BZ3_STAGE_CM] == 1)
         cm_encode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+    else if (s->variant[BZ3_STAGE_CM] == 2)
+        cm_encode_chunked_kernel<1><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+    else if (s->variant[BZ3_STAGE_CM] == 3)
+        cm_encode_chunked_kernel<2><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     else
-        cm_encode_chunked_kernel<<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+        cm_encode_chunked_kernel<0><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 12, d_res, 4, cudaMemcpyDeviceToHost, s->stream));

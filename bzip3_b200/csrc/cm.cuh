@@ -187,33 +187,86 @@ constexpr int kCmEncChunk = 1024;
 constexpr int kCmEncThreads = 64;
 constexpr size_t kCmEncSmemBytes = (size_t)kCmTableU16 * 2 + 2 * (size_t)kCmEncChunk * 8 * 4 + 2 * (size_t)kCmEncChunk + 64;
 
-struct RcEnc {
+// mul.hi that the compiler may neither sink into a branch nor drop: it is issued speculatively for the
+// NEXT decision before the (rare) renormalisation test of the current one has resolved, which takes the
+// test off the critical recurrence  range -> mul.hi -> range.
+BZ_D u32 mulhi_pinned(u32 a, u32 b) {
+    u32 r;
+    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+// out-of-line renormalisation: returns (low, range, op) after emitting every settled byte
+struct RcState {
     u32 low, range;
     s32 op;
 };
-BZ_D void rc_encode_entry(RcEnc& rc, u32 e, u8* __restrict__ out) {
-    const u32 x = __umulhi(rc.range, e & 0xFFFFC000u);
-    if (e & 1u) {
-        rc.range = x;
+__device__ __noinline__ RcState rc_renorm_outlined(u32 low, u32 high, s32 op, u8* out) {
+    do {
+        out[op++] = (u8)(low >> 24);
+        low <<= 8;
+        high = (high << 8) | 0xFFu;
+    } while ((low ^ high) < (1u << 24));
+    RcState r;
+    r.low = low;
+    r.range = high - low;
+    r.op = op;
+    return r;
+}
+
+// MODE 0: inline loop.  MODE 1: out-of-line call (fast path falls through).  MODE 2: first shift predicated.
+template <int MODE>
+BZ_D void rc_step(u32& low, u32& range, u32& x, s32& op, bool bit, u32 mnext, u8* __restrict__ out) {
+    if (bit) {
+        range = x;
     } else {
-        rc.low += x + 1u;
-        rc.range -= x + 1u;
+        low += x + 1u;
+        range -= x + 1u;
     }
-    if (rc.range < (1u << 24)) {
-        u32 high = rc.low + rc.range;
-        while ((rc.low ^ high) < (1u << 24)) {
-            out[rc.op++] = (u8)(rc.low >> 24);
-            rc.low <<= 8;
-            high = (high << 8) | 0xFFu;
+    x = mulhi_pinned(range, mnext);
+    u32 high = low + range;
+    if (MODE == 0) {
+        if ((low ^ high) < (1u << 24)) {
+            do {
+                out[op++] = (u8)(low >> 24);
+                low <<= 8;
+                high = (high << 8) | 0xFFu;
+            } while ((low ^ high) < (1u << 24));
+            range = high - low;
+            x = mulhi_pinned(range, mnext);
         }
-        rc.range = high - rc.low;
+    } else if (MODE == 1) {
+        if ((low ^ high) < (1u << 24)) {
+            const RcState r = rc_renorm_outlined(low, high, op, out);
+            low = r.low;
+            range = r.range;
+            op = r.op;
+            x = mulhi_pinned(range, mnext);
+        }
+    } else {
+        const bool need = (low ^ high) < (1u << 24);
+        if (need) out[op] = (u8)(low >> 24);
+        op += need ? 1 : 0;
+        low = need ? (low << 8) : low;
+        high = need ? ((high << 8) | 0xFFu) : high;
+        range = high - low;
+        if (need) {  // the speculative product is stale; a second shift in a row is rare
+            while ((low ^ high) < (1u << 24)) {
+                out[op++] = (u8)(low >> 24);
+                low <<= 8;
+                high = (high << 8) | 0xFFu;
+            }
+            range = high - low;
+            x = mulhi_pinned(range, mnext);
+        }
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const u8* __restrict__ in, s32 n,
                                                                          u8* __restrict__ out, s32* out_size) {
     extern __shared__ __align__(16) u16 cm_smem[];
-    u32* pbuf = reinterpret_cast<u32*>(cm_smem + kCmTableU16);           // [2][kCmEncChunk * 8]
+    u32* pbuf = reinterpret_cast<u32*>(cm_smem + kCmTableU16);           // [2][kCmEncChunk * 8]  P << 14
     u8* sbytes = reinterpret_cast<u8*>(pbuf + 2 * kCmEncChunk * 8);      // [2][kCmEncChunk]
     cm_tables_init_smem(cm_smem);
     __syncthreads();
@@ -222,7 +275,8 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
     const s32 nchunks = (n + kCmEncChunk - 1) / kCmEncChunk;
     const CmTables t = cm_tables_at(cm_smem);
     CmCtx c{0, 0, 0, 0u};
-    RcEnc rc{0u, 0xFFFFFFFFu, 0};
+    u32 low = 0, range = 0xFFFFFFFFu;
+    s32 op = 0;
     for (s32 it = 0; it <= nchunks; it++) {
         if (warp == 0 && it < nchunks) {
             const s32 base = it * kCmEncChunk;
@@ -238,8 +292,7 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                     cm_ctx_begin_byte(c);
                     const int node = top | (sym >> sh_node);
                     const int bit = (sym >> sh_bit) & 1;
-                    const u32 P = cm_code_known_bit(t, node, c, bit);
-                    pb[k * 8] = (P << 14) | (u32)bit;
+                    pb[k * 8] = cm_code_known_bit(t, node, c, bit) << 14;
                     cm_ctx_end_byte(c, sym);
                 }
             }
@@ -247,30 +300,38 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
             const s32 base = (it - 1) * kCmEncChunk;
             const s32 len = (n - base) < kCmEncChunk ? (n - base) : kCmEncChunk;
             const uint4* pv = reinterpret_cast<const uint4*>(pbuf + ((it - 1) & 1) * (kCmEncChunk * 8));
+            const u8* sb = sbytes + ((it - 1) & 1) * kCmEncChunk;
             uint4 a = pv[0], b = pv[1];
+            u32 sym = sb[0];
+            u32 x = mulhi_pinned(range, a.x);
             for (s32 k = 0; k < len; k++) {
                 const uint4 ca = a, cb = b;
-                if (k + 1 < len) { a = pv[2 * k + 2]; b = pv[2 * k + 3]; }
-                rc_encode_entry(rc, ca.x, out);
-                rc_encode_entry(rc, ca.y, out);
-                rc_encode_entry(rc, ca.z, out);
-                rc_encode_entry(rc, ca.w, out);
-                rc_encode_entry(rc, cb.x, out);
-                rc_encode_entry(rc, cb.y, out);
-                rc_encode_entry(rc, cb.z, out);
-                rc_encode_entry(rc, cb.w, out);
+                const u32 cs = sym;
+                const s32 kn = (k + 1 < len) ? k + 1 : k;  // the last byte re-reads itself; its look-ahead product is unused
+                a = pv[2 * kn];
+                b = pv[2 * kn + 1];
+                sym = sb[kn];
+                rc_step<MODE>(low, range, x, op, cs & 0x80u, ca.y, out);
+                rc_step<MODE>(low, range, x, op, cs & 0x40u, ca.z, out);
+                rc_step<MODE>(low, range, x, op, cs & 0x20u, ca.w, out);
+                rc_step<MODE>(low, range, x, op, cs & 0x10u, cb.x, out);
+                rc_step<MODE>(low, range, x, op, cs & 0x08u, cb.y, out);
+                rc_step<MODE>(low, range, x, op, cs & 0x04u, cb.z, out);
+                rc_step<MODE>(low, range, x, op, cs & 0x02u, cb.w, out);
+                rc_step<MODE>(low, range, x, op, cs & 0x01u, a.x, out);
             }
         }
         __syncthreads();
     }
     if (threadIdx.x == 32) {
         for (int k = 0; k < 4; k++) {  // flush (reference src/libbz3.c:425-432)
-            out[rc.op++] = (u8)(rc.low >> 24);
-            rc.low <<= 8;
+            out[op++] = (u8)(low >> 24);
+            low <<= 8;
         }
-        *out_size = rc.op;
+        *out_size = op;
     }
 }
+
 
 // ---- tree-parallel decoder ---------------------------------------------------------------------
 // Decoding is one dependent chain: the next context depends on the bit just decoded.  What does not
@@ -310,6 +371,12 @@ BZ_D void cm_node_learn(const CmTables& t, int node, const NodeCalc& k, int bit)
     k.row[1] = (u16)cm_adapt((u32)k.hi, bit, 6);
 }
 
+// branch-free counter update: bit ? v + ((v ^ 65535) >> rate) : v - (v >> rate)
+BZ_D u32 cm_adapt_bf(u32 v, u32 ones /* bit ? 0xFFFF : 0 */, int rate) {
+    const u32 u = (v ^ ones) >> rate;
+    return ones ? v + u : v - u;
+}
+
 __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8* __restrict__ in, s32 insize,
                                                                       u8* __restrict__ out, s32 n) {
     extern __shared__ __align__(16) u16 cm_smem[];
@@ -319,9 +386,15 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
     const int tid = threadIdx.x;
     for (int k = tid; k < 2048; k += kCmDecThreads) scode[k] = (k < insize) ? in[k] : 0;
     __syncthreads();
-    const CmTables t = cm_tables_at(cm_smem);
+    // thread `tid` owns nodes tid (depth 0..6, tid >= 1) and tid + 128 (depth 7)
     const int nodeA = tid, nodeB = tid + 128;
-    const int depthA = tid ? 31 - __clz(tid) : 0;
+    const int shA = tid ? 8 - (31 - __clz(tid)) : 8;      // (256|byte) >> shA == nodeA  <=> nodeA is on the path
+    u16* const c0A = cm_smem + nodeA;
+    u16* const c0B = cm_smem + nodeB;
+    u16* const c1A = cm_smem + kCmC0 + nodeA;             // + prev * 256
+    u16* const c1B = cm_smem + kCmC0 + nodeB;
+    u16* const rowA = cm_smem + kCmC0 + kCmC1 + (2 * nodeA) * 17;   // + flag * 17 + cell
+    u16* const rowB = cm_smem + kCmC0 + kCmC1 + (2 * nodeB) * 17;
     s32 wlo = 0;  // the window holds stream bytes [wlo, wlo + 2048)
     s32 ip = 0;
     u32 low = 0, range = 0xFFFFFFFFu, code = 0;
@@ -337,43 +410,77 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         run = (prev1 == prev2) ? run + 1 : 0;
         const int flag = run > 2;
         u32* pt = ptab + (i & 1) * 256;
-        NodeCalc ka, kb;
-        if (tid) pt[nodeA] = cm_node_predict(t, nodeA, prev1, prev2, flag, ka) << 14;
-        pt[nodeB] = cm_node_predict(t, nodeB, prev1, prev2, flag, kb) << 14;
+        // ---- A: probabilities of both owned nodes (the two chains interleave)
+        u16* const q1A = c1A + prev1 * 256;
+        u16* const q1B = c1B + prev1 * 256;
+        const int aA = *c0A, aB = *c0B;
+        const int bA = *q1A, bB = *q1B;
+        const int dA = c1A[prev2 * 256], dB = c1B[prev2 * 256];
+        const int pA = ((aA + bA) * 7 + dA + dA) >> 4;
+        const int pB = ((aB + bB) * 7 + dB + dB) >> 4;
+        u16* const cellA = rowA + flag * 17 + (pA >> 12);
+        u16* const cellB = rowB + flag * 17 + (pB >> 12);
+        const int loA = cellA[0], hiA = cellA[1];
+        const int loB = cellB[0], hiB = cellB[1];
+        const int sseA = loA + (((hiA - loA) * (pA & 4095)) >> 12);
+        const int sseB = loB + (((hiB - loB) * (pB & 4095)) >> 12);
+        pt[nodeA] = (u32)(sseA * 3 + pA) << 14;   // slot 0 is never read
+        pt[nodeB] = (u32)(sseB * 3 + pB) << 14;
         __syncthreads();
-        // ---- B: the serial chain, identical in every thread
-        int node = 1;
-        u32 pcur = pt[1];
-        uint2 kids = *reinterpret_cast<const uint2*>(pt + 2);
+        // ---- B: the serial chain, identical in every thread.  pcur = P(node), kids = P(children of node),
+        //         gk = P(grandchildren of node); the 4 grandchildren are one aligned 128-bit row of ptab.
+        const uint4 g0 = *reinterpret_cast<const uint4*>(pt);
+        uint4 gk = *reinterpret_cast<const uint4*>(pt + 4);
+        u32 pcur = g0.y;
+        u32 kid0 = g0.z, kid1 = g0.w;
+        u32 node = 1;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const u32 x = __umulhi(range, pcur);
             const u32 mid = low + x;
             const bool bit = code <= mid;
-            node = node * 2 + (bit ? 1 : 0);
-            pcur = bit ? kids.y : kids.x;
-            if (k < 6) kids = *reinterpret_cast<const uint2*>(pt + 2 * node);
+            node = node * 2 + (bit ? 1u : 0u);
+            pcur = bit ? kid1 : kid0;
+            kid0 = bit ? gk.z : gk.x;
+            kid1 = bit ? gk.w : gk.y;
+            if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
             range = bit ? x : range - x - 1u;
             low = bit ? low : mid + 1u;
-            if (range < (1u << 24)) {
-                u32 high = low + range;
-                while ((low ^ high) < (1u << 24)) {
+            u32 high = low + range;
+            if (__builtin_expect((low ^ high) < (1u << 24), 0)) {
+                do {
                     low <<= 8;
                     high = (high << 8) | 0xFFu;
                     const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;
                     ip += (ip < insize);
                     code = (code << 8) + add;
-                }
+                } while ((low ^ high) < (1u << 24));
                 range = high - low;
             }
         }
-        const int byte = node & 255;
-        // ---- C: owners of the visited nodes learn
-        if (tid && nodeA == ((256 | byte) >> (8 - depthA))) cm_node_learn(t, nodeA, ka, (byte >> (7 - depthA)) & 1);
-        if (nodeB == (128 | (byte >> 1))) cm_node_learn(t, nodeB, kb, byte & 1);
+        const u32 byte = node & 255u;
+        // ---- C: owners of the visited nodes learn (branch-free arithmetic, predicated stores)
+        {
+            const bool onA = tid != 0 && ((256u | byte) >> shA) == (u32)nodeA;
+            const u32 onesA = ((byte >> (shA - 1)) & 1u) ? 0xFFFFu : 0u;
+            if (onA) {
+                *c0A = (u16)cm_adapt_bf((u32)aA, onesA, 2);
+                *q1A = (u16)cm_adapt_bf((u32)bA, onesA, 4);
+                cellA[0] = (u16)cm_adapt_bf((u32)loA, onesA, 6);
+                cellA[1] = (u16)cm_adapt_bf((u32)hiA, onesA, 6);
+            }
+            const bool onB = (128u | (byte >> 1)) == (u32)nodeB;
+            const u32 onesB = (byte & 1u) ? 0xFFFFu : 0u;
+            if (onB) {
+                *c0B = (u16)cm_adapt_bf((u32)aB, onesB, 2);
+                *q1B = (u16)cm_adapt_bf((u32)bB, onesB, 4);
+                cellB[0] = (u16)cm_adapt_bf((u32)loB, onesB, 6);
+                cellB[1] = (u16)cm_adapt_bf((u32)hiB, onesB, 6);
+            }
+        }
         if (tid == 0) out[i] = (u8)byte;
         prev2 = prev1;
-        prev1 = byte;
+        prev1 = (int)byte;
         if (ip - wlo >= 1024) {  // uniform: every thread follows the same chain
             __syncthreads();
             for (int k = tid; k < 1024; k += kCmDecThreads) {
@@ -389,7 +496,9 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
 inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
-    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     return cudaSuccess;
 }

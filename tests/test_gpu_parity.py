@@ -152,13 +152,13 @@ def test_stage_unbwt_on_garbage_matches_reference_semantics(st, O):
         assert bytes(got[:n]) == bytes(want[:n]), (t, n, k, idx, first_diff(got[:n], want[:n]))
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["parallel", "single"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["parallel", "single", "outlined", "predicated"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_stage_cm(st, O, name, data, variant):
     a = arr(data)
     n = len(a)
-    if variant == 1 and n > 120_000:
-        pytest.skip("single-lane cross-check kernel kept to small inputs")
+    if variant >= 1 and n > 120_000:
+        pytest.skip("cross-check kernel variants kept to small inputs")
     pad = np.zeros(n + 16, np.uint8)
     pad[:n] = a
     want = np.zeros(2 * n + 64, np.uint8)
