@@ -118,15 +118,14 @@ struct Timer {
         s->clk.used[stage] = true;
     }
 };
-void clocks_begin(bz3_state* s) {
-    for (int i = 0; i < BZ3_STAGE_COUNT; i++) s->clk.used[i] = false;
-}
+void clocks_begin(bz3_state*) {}  // entries reset themselves when collected
 void clocks_collect(bz3_state* s, int decode) {
     cudaStreamSynchronize(s->stream);
     for (int i = 0; i < BZ3_STAGE_COUNT; i++)
         if (s->clk.used[i]) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, s->clk.a[i], s->clk.b[i]) == cudaSuccess) s->stage_ms[decode][i] += ms;
+            s->clk.used[i] = false;  // collected once
         }
 }
 
@@ -266,7 +265,7 @@ cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s
     if (s->variant[BZ3_STAGE_CM] == 1)
         cm_decode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else
-        cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n, 0u);
     BZ_NOTE_LAUNCH();
     return cudaGetLastError();
 }

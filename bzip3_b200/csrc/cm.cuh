@@ -196,17 +196,19 @@ BZ_D u32 mulhi_pinned(u32 a, u32 b) {
     return r;
 }
 
-// out-of-line renormalisation: returns (low, range, op) after emitting every settled byte
+// out-of-line renormalisation: returns (low, range, op) after emitting every settled byte.  Entered
+// whenever range < 2^24 (necessary for the top bytes of low and low+range to agree), may emit nothing.
 struct RcState {
     u32 low, range;
     s32 op;
 };
-__device__ __noinline__ RcState rc_renorm_outlined(u32 low, u32 high, s32 op, u8* out) {
-    do {
+__device__ __noinline__ RcState rc_renorm_outlined(u32 low, u32 range, s32 op, u8* out) {
+    u32 high = low + range;
+    while ((low ^ high) < (1u << 24)) {
         out[op++] = (u8)(low >> 24);
         low <<= 8;
         high = (high << 8) | 0xFFu;
-    } while ((low ^ high) < (1u << 24));
+    }
     RcState r;
     r.low = low;
     r.range = high - low;
@@ -214,9 +216,39 @@ __device__ __noinline__ RcState rc_renorm_outlined(u32 low, u32 high, s32 op, u8
     return r;
 }
 
-// MODE 0: inline loop.  MODE 1: out-of-line call (fast path falls through).  MODE 2: first shift predicated.
+// One coding decision.  `x` enters holding umulhi(range, P<<14) for THIS decision and leaves holding the
+// product for the NEXT one (multiplier mnext), issued before anything that is not on the recurrence
+// range -> mul.hi -> range.  The instruction order inside the asm block is the schedule: a single
+// in-order thread pays ~4 cycles for every dependent instruction placed ahead of the multiply.
+// MODE 0: hand-ordered PTX.  MODE 1/2: compiler-scheduled C (kept for comparison).
 template <int MODE>
-BZ_D void rc_step(u32& low, u32& range, u32& x, s32& op, bool bit, u32 mnext, u8* __restrict__ out) {
+BZ_D void rc_step(u32& low, u32& range, u32& x, s32& op, u32 bit, u32 mnext, u8* __restrict__ out) {
+    if (MODE == 0) {
+        u32 slow;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pb, ps;\n\t"
+            ".reg .u32 nx;\n\t"
+            "setp.ne.u32 pb, %4, 0;\n\t"
+            "not.b32 nx, %2;\n\t"
+            "@pb mov.u32 %1, %2;\n\t"          // bit 1: range = x
+            "@!pb add.u32 %1, %1, nx;\n\t"     // bit 0: range -= x + 1
+            "mul.hi.u32 %2, %1, %5;\n\t"       // product for the next decision
+            "@!pb sub.u32 %0, %0, nx;\n\t"     // bit 0: low += x + 1
+            "setp.lt.u32 ps, %1, 0x1000000;\n\t"
+            "selp.u32 %3, 1, 0, ps;\n\t"
+            "}"
+            : "+r"(low), "+r"(range), "+r"(x), "=r"(slow)
+            : "r"(bit), "r"(mnext));
+        if (slow) {
+            const RcState r = rc_renorm_outlined(low, range, op, out);
+            low = r.low;
+            range = r.range;
+            op = r.op;
+            x = mulhi_pinned(range, mnext);
+        }
+        return;
+    }
     if (bit) {
         range = x;
     } else {
@@ -224,38 +256,22 @@ BZ_D void rc_step(u32& low, u32& range, u32& x, s32& op, bool bit, u32 mnext, u8
         range -= x + 1u;
     }
     x = mulhi_pinned(range, mnext);
-    u32 high = low + range;
-    if (MODE == 0) {
-        if ((low ^ high) < (1u << 24)) {
-            do {
-                out[op++] = (u8)(low >> 24);
-                low <<= 8;
-                high = (high << 8) | 0xFFu;
-            } while ((low ^ high) < (1u << 24));
-            range = high - low;
-            x = mulhi_pinned(range, mnext);
-        }
-    } else if (MODE == 1) {
-        if ((low ^ high) < (1u << 24)) {
-            const RcState r = rc_renorm_outlined(low, high, op, out);
+    if (MODE == 1) {
+        if (range < (1u << 24)) {
+            const RcState r = rc_renorm_outlined(low, range, op, out);
             low = r.low;
             range = r.range;
             op = r.op;
             x = mulhi_pinned(range, mnext);
         }
     } else {
-        const bool need = (low ^ high) < (1u << 24);
-        if (need) out[op] = (u8)(low >> 24);
-        op += need ? 1 : 0;
-        low = need ? (low << 8) : low;
-        high = need ? ((high << 8) | 0xFFu) : high;
-        range = high - low;
-        if (need) {  // the speculative product is stale; a second shift in a row is rare
-            while ((low ^ high) < (1u << 24)) {
+        u32 high = low + range;
+        if ((low ^ high) < (1u << 24)) {
+            do {
                 out[op++] = (u8)(low >> 24);
                 low <<= 8;
                 high = (high << 8) | 0xFFu;
-            }
+            } while ((low ^ high) < (1u << 24));
             range = high - low;
             x = mulhi_pinned(range, mnext);
         }
@@ -378,7 +394,7 @@ BZ_D u32 cm_adapt_bf(u32 v, u32 ones /* bit ? 0xFFFF : 0 */, int rate) {
 }
 
 __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8* __restrict__ in, s32 insize,
-                                                                      u8* __restrict__ out, s32 n) {
+                                                                      u8* __restrict__ out, s32 n, u32 zero) {
     extern __shared__ __align__(16) u16 cm_smem[];
     u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [2][256]
     u8* scode = reinterpret_cast<u8*>(ptab + 512);              // [2048] window of the compressed stream
@@ -434,28 +450,48 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         u32 pcur = g0.y;
         u32 kid0 = g0.z, kid1 = g0.w;
         u32 node = 1;
+        u32 x = mulhi_pinned(range, pcur);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const u32 x = __umulhi(range, pcur);
-            const u32 mid = low + x;
-            const bool bit = code <= mid;
-            node = node * 2 + (bit ? 1u : 0u);
-            pcur = bit ? kid1 : kid0;
+            // x holds umulhi(range, P(node)).  The block decides the bit, updates (low, range), selects the
+            // child's probability and immediately issues the multiply of the NEXT step; table prefetch, node
+            // bookkeeping and the renormalisation test follow it in program order.
+            u32 bit, slow;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred pb, ps;\n\t"
+                ".reg .u32 mid, nx, r0;\n\t"
+                "add.u32 mid, %0, %2;\n\t"
+                "not.b32 nx, %2;\n\t"
+                "setp.le.u32 pb, %6, mid;\n\t"        // bit = code <= low + x
+                "add.u32 r0, %1, nx;\n\t"             // range - x - 1, ready before the bit is
+                "selp.u32 %1, %2, r0, pb;\n\t"        // bit ? x : range - x - 1
+                "selp.u32 %3, %8, %7, pb;\n\t"        // P of the chosen child
+                "mul.hi.u32 %2, %1, %3;\n\t"          // product for the next step
+                "@!pb add.u32 %0, mid, 1;\n\t"        // bit 0: low = mid + 1
+                "selp.u32 %4, 1, 0, pb;\n\t"
+                "and.b32 nx, %2, %9;\n\t"           // %9 is a run-time zero: ties the bookkeeping below to the
+                "or.b32 %4, %4, nx;\n\t"            // multiply so the assembler cannot schedule it ahead of it
+                "setp.lt.u32 ps, %1, 0x1000000;\n\t"
+                "selp.u32 %5, 1, 0, ps;\n\t"
+                "}"
+                : "+r"(low), "+r"(range), "+r"(x), "+r"(pcur), "=r"(bit), "=r"(slow)
+                : "r"(code), "r"(kid0), "r"(kid1), "r"(zero));
+            node = node * 2 + bit;
             kid0 = bit ? gk.z : gk.x;
             kid1 = bit ? gk.w : gk.y;
             if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
-            range = bit ? x : range - x - 1u;
-            low = bit ? low : mid + 1u;
-            u32 high = low + range;
-            if (__builtin_expect((low ^ high) < (1u << 24), 0)) {
-                do {
+            if (slow) {
+                u32 high = low + range;
+                while ((low ^ high) < (1u << 24)) {
                     low <<= 8;
                     high = (high << 8) | 0xFFu;
                     const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;
                     ip += (ip < insize);
                     code = (code << 8) + add;
-                } while ((low ^ high) < (1u << 24));
+                }
                 range = high - low;
+                x = mulhi_pinned(range, pcur);
             }
         }
         const u32 byte = node & 255u;
