@@ -249,8 +249,6 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
         cm_encode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     else if (s->variant[BZ3_STAGE_CM] == 2)
         cm_encode_chunked_kernel<1><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
-    else if (s->variant[BZ3_STAGE_CM] == 3)
-        cm_encode_chunked_kernel<2><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     else
         cm_encode_chunked_kernel<0><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     BZ_NOTE_LAUNCH();
@@ -265,7 +263,7 @@ cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s
     if (s->variant[BZ3_STAGE_CM] == 1)
         cm_decode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else
-        cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n, 0u);
+        cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     BZ_NOTE_LAUNCH();
     return cudaGetLastError();
 }

@@ -196,86 +196,48 @@ BZ_D u32 mulhi_pinned(u32 a, u32 b) {
     return r;
 }
 
-// out-of-line renormalisation: returns (low, range, op) after emitting every settled byte.  Entered
-// whenever range < 2^24 (necessary for the top bytes of low and low+range to agree), may emit nothing.
-struct RcState {
-    u32 low, range;
-    s32 op;
-};
-__device__ __noinline__ RcState rc_renorm_outlined(u32 low, u32 range, s32 op, u8* out) {
-    u32 high = low + range;
-    while ((low ^ high) < (1u << 24)) {
-        out[op++] = (u8)(low >> 24);
-        low <<= 8;
-        high = (high << 8) | 0xFFu;
-    }
-    RcState r;
-    r.low = low;
-    r.range = high - low;
-    r.op = op;
-    return r;
+// ---- range coder lane -------------------------------------------------------------------------
+// Measured on B200 (profiles/r01_ncu_source_cm_*): for one in-order thread a TAKEN branch costs ~28
+// cycles and every dependent ALU instruction ~4-5, so the byte is coded in two tiers:
+//   fast tier   eight decisions with no branch at all.  No renormalisation is applied; instead the
+//               minimum over the eight steps of  low ^ (low + range)  is kept.  If it never dropped below
+//               2^24 no byte had to be shifted out and the result is exact.
+//   exact tier  otherwise the byte is redone from its saved start state with the reference loop.
+// For BWT output most bytes take the fast tier (a byte is shifted out every ~40 decisions).
+// Recurrence in (low, range) form:  x = umulhi(range, P << 14)  ( == (range * P) >> 18 ),
+//     bit 1: range = x            bit 0: low += x + 1, range -= x + 1
+BZ_D void rc_fast_step(u32& low, u32& range, u32& x, u32& tmin, u32 bit, u32 mnext) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pb;\n\t"
+        ".reg .u32 nx, hi, t;\n\t"
+        "setp.ne.u32 pb, %4, 0;\n\t"
+        "not.b32 nx, %2;\n\t"
+        "@pb mov.u32 %1, %2;\n\t"          // bit 1: range = x
+        "@!pb add.u32 %1, %1, nx;\n\t"     // bit 0: range -= x + 1
+        "mul.hi.u32 %2, %1, %5;\n\t"       // product for the next decision
+        "@!pb sub.u32 %0, %0, nx;\n\t"     // bit 0: low += x + 1
+        "add.u32 hi, %0, %1;\n\t"
+        "xor.b32 t, %0, hi;\n\t"
+        "min.u32 %3, %3, t;\n\t"
+        "}"
+        : "+r"(low), "+r"(range), "+r"(x), "+r"(tmin)
+        : "r"(bit), "r"(mnext));
 }
 
-// One coding decision.  `x` enters holding umulhi(range, P<<14) for THIS decision and leaves holding the
-// product for the NEXT one (multiplier mnext), issued before anything that is not on the recurrence
-// range -> mul.hi -> range.  The instruction order inside the asm block is the schedule: a single
-// in-order thread pays ~4 cycles for every dependent instruction placed ahead of the multiply.
-// MODE 0: hand-ordered PTX.  MODE 1/2: compiler-scheduled C (kept for comparison).
-template <int MODE>
-BZ_D void rc_step(u32& low, u32& range, u32& x, s32& op, u32 bit, u32 mnext, u8* __restrict__ out) {
-    if (MODE == 0) {
-        u32 slow;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred pb, ps;\n\t"
-            ".reg .u32 nx;\n\t"
-            "setp.ne.u32 pb, %4, 0;\n\t"
-            "not.b32 nx, %2;\n\t"
-            "@pb mov.u32 %1, %2;\n\t"          // bit 1: range = x
-            "@!pb add.u32 %1, %1, nx;\n\t"     // bit 0: range -= x + 1
-            "mul.hi.u32 %2, %1, %5;\n\t"       // product for the next decision
-            "@!pb sub.u32 %0, %0, nx;\n\t"     // bit 0: low += x + 1
-            "setp.lt.u32 ps, %1, 0x1000000;\n\t"
-            "selp.u32 %3, 1, 0, ps;\n\t"
-            "}"
-            : "+r"(low), "+r"(range), "+r"(x), "=r"(slow)
-            : "r"(bit), "r"(mnext));
-        if (slow) {
-            const RcState r = rc_renorm_outlined(low, range, op, out);
-            low = r.low;
-            range = r.range;
-            op = r.op;
-            x = mulhi_pinned(range, mnext);
-        }
-        return;
-    }
-    if (bit) {
-        range = x;
-    } else {
-        low += x + 1u;
-        range -= x + 1u;
-    }
-    x = mulhi_pinned(range, mnext);
-    if (MODE == 1) {
-        if (range < (1u << 24)) {
-            const RcState r = rc_renorm_outlined(low, range, op, out);
-            low = r.low;
-            range = r.range;
-            op = r.op;
-            x = mulhi_pinned(range, mnext);
-        }
-    } else {
-        u32 high = low + range;
-        if ((low ^ high) < (1u << 24)) {
-            do {
-                out[op++] = (u8)(low >> 24);
-                low <<= 8;
-                high = (high << 8) | 0xFFu;
-            } while ((low ^ high) < (1u << 24));
-            range = high - low;
-            x = mulhi_pinned(range, mnext);
+// exact tier: the reference recurrence for the 8 decisions of one byte; m = the byte's 8 multipliers
+__device__ __noinline__ uint4 rc_exact_byte(u32 low, u32 range, s32 op, u32 sym, const u32* m, u8* out) {
+    u32 high = low + range;
+    for (int j = 0; j < 8; j++) {
+        const u32 x = __umulhi(high - low, m[j]);
+        if ((sym << j) & 0x80u) high = low + x; else low += x + 1u;
+        while ((low ^ high) < (1u << 24)) {
+            out[op++] = (u8)(low >> 24);
+            low <<= 8;
+            high = (high << 8) | 0xFFu;
         }
     }
+    return make_uint4(low, high - low, (u32)op, 0u);
 }
 
 template <int MODE>
@@ -315,7 +277,8 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
         } else if (warp == 1 && lane == 0 && it > 0) {
             const s32 base = (it - 1) * kCmEncChunk;
             const s32 len = (n - base) < kCmEncChunk ? (n - base) : kCmEncChunk;
-            const uint4* pv = reinterpret_cast<const uint4*>(pbuf + ((it - 1) & 1) * (kCmEncChunk * 8));
+            const u32* pw = pbuf + ((it - 1) & 1) * (kCmEncChunk * 8);
+            const uint4* pv = reinterpret_cast<const uint4*>(pw);
             const u8* sb = sbytes + ((it - 1) & 1) * kCmEncChunk;
             uint4 a = pv[0], b = pv[1];
             u32 sym = sb[0];
@@ -327,14 +290,30 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                 a = pv[2 * kn];
                 b = pv[2 * kn + 1];
                 sym = sb[kn];
-                rc_step<MODE>(low, range, x, op, cs & 0x80u, ca.y, out);
-                rc_step<MODE>(low, range, x, op, cs & 0x40u, ca.z, out);
-                rc_step<MODE>(low, range, x, op, cs & 0x20u, ca.w, out);
-                rc_step<MODE>(low, range, x, op, cs & 0x10u, cb.x, out);
-                rc_step<MODE>(low, range, x, op, cs & 0x08u, cb.y, out);
-                rc_step<MODE>(low, range, x, op, cs & 0x04u, cb.z, out);
-                rc_step<MODE>(low, range, x, op, cs & 0x02u, cb.w, out);
-                rc_step<MODE>(low, range, x, op, cs & 0x01u, a.x, out);
+                if (MODE == 0) {
+                    const u32 low0 = low, range0 = range;
+                    u32 tmin = 0xFFFFFFFFu;
+                    rc_fast_step(low, range, x, tmin, cs & 0x80u, ca.y);
+                    rc_fast_step(low, range, x, tmin, cs & 0x40u, ca.z);
+                    rc_fast_step(low, range, x, tmin, cs & 0x20u, ca.w);
+                    rc_fast_step(low, range, x, tmin, cs & 0x10u, cb.x);
+                    rc_fast_step(low, range, x, tmin, cs & 0x08u, cb.y);
+                    rc_fast_step(low, range, x, tmin, cs & 0x04u, cb.z);
+                    rc_fast_step(low, range, x, tmin, cs & 0x02u, cb.w);
+                    rc_fast_step(low, range, x, tmin, cs & 0x01u, a.x);
+                    if (tmin < (1u << 24)) {  // some decision needed a shift: redo this byte exactly
+                        const uint4 r = rc_exact_byte(low0, range0, op, cs, pw + 8 * k, out);
+                        low = r.x;
+                        range = r.y;
+                        op = (s32)r.z;
+                        x = mulhi_pinned(range, a.x);
+                    }
+                } else {
+                    const uint4 r = rc_exact_byte(low, range, op, cs, pw + 8 * k, out);
+                    low = r.x;
+                    range = r.y;
+                    op = (s32)r.z;
+                }
             }
         }
         __syncthreads();
@@ -347,7 +326,6 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
         *out_size = op;
     }
 }
-
 
 // ---- tree-parallel decoder ---------------------------------------------------------------------
 // Decoding is one dependent chain: the next context depends on the bit just decoded.  What does not
@@ -394,7 +372,7 @@ BZ_D u32 cm_adapt_bf(u32 v, u32 ones /* bit ? 0xFFFF : 0 */, int rate) {
 }
 
 __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8* __restrict__ in, s32 insize,
-                                                                      u8* __restrict__ out, s32 n, u32 zero) {
+                                                                      u8* __restrict__ out, s32 n) {
     extern __shared__ __align__(16) u16 cm_smem[];
     u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [2][256]
     u8* scode = reinterpret_cast<u8*>(ptab + 512);              // [2048] window of the compressed stream
@@ -447,51 +425,61 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         //         gk = P(grandchildren of node); the 4 grandchildren are one aligned 128-bit row of ptab.
         const uint4 g0 = *reinterpret_cast<const uint4*>(pt);
         uint4 gk = *reinterpret_cast<const uint4*>(pt + 4);
-        u32 pcur = g0.y;
-        u32 kid0 = g0.z, kid1 = g0.w;
         u32 node = 1;
-        u32 x = mulhi_pinned(range, pcur);
+        {
+            // fast tier: 8 branch-free steps on copies of the state, assuming no renormalisation is needed
+            u32 flow = low, frange = range;
+            u32 pcur = g0.y, kid0 = g0.z, kid1 = g0.w;
+            u32 x = mulhi_pinned(frange, pcur);
+            u32 tmin = 0xFFFFFFFFu;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            // x holds umulhi(range, P(node)).  The block decides the bit, updates (low, range), selects the
-            // child's probability and immediately issues the multiply of the NEXT step; table prefetch, node
-            // bookkeeping and the renormalisation test follow it in program order.
-            u32 bit, slow;
-            asm volatile(
-                "{\n\t"
-                ".reg .pred pb, ps;\n\t"
-                ".reg .u32 mid, nx, r0;\n\t"
-                "add.u32 mid, %0, %2;\n\t"
-                "not.b32 nx, %2;\n\t"
-                "setp.le.u32 pb, %6, mid;\n\t"        // bit = code <= low + x
-                "add.u32 r0, %1, nx;\n\t"             // range - x - 1, ready before the bit is
-                "selp.u32 %1, %2, r0, pb;\n\t"        // bit ? x : range - x - 1
-                "selp.u32 %3, %8, %7, pb;\n\t"        // P of the chosen child
-                "mul.hi.u32 %2, %1, %3;\n\t"          // product for the next step
-                "@!pb add.u32 %0, mid, 1;\n\t"        // bit 0: low = mid + 1
-                "selp.u32 %4, 1, 0, pb;\n\t"
-                "and.b32 nx, %2, %9;\n\t"           // %9 is a run-time zero: ties the bookkeeping below to the
-                "or.b32 %4, %4, nx;\n\t"            // multiply so the assembler cannot schedule it ahead of it
-                "setp.lt.u32 ps, %1, 0x1000000;\n\t"
-                "selp.u32 %5, 1, 0, ps;\n\t"
-                "}"
-                : "+r"(low), "+r"(range), "+r"(x), "+r"(pcur), "=r"(bit), "=r"(slow)
-                : "r"(code), "r"(kid0), "r"(kid1), "r"(zero));
-            node = node * 2 + bit;
-            kid0 = bit ? gk.z : gk.x;
-            kid1 = bit ? gk.w : gk.y;
-            if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
-            if (slow) {
+            for (int k = 0; k < 8; k++) {
+                u32 bit;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pb;\n\t"
+                    ".reg .u32 mid, nx, r0, hi, t;\n\t"
+                    "add.u32 mid, %0, %2;\n\t"
+                    "not.b32 nx, %2;\n\t"
+                    "setp.le.u32 pb, %6, mid;\n\t"        // bit = code <= low + x
+                    "add.u32 r0, %1, nx;\n\t"             // range - x - 1
+                    "selp.u32 %1, %2, r0, pb;\n\t"        // bit ? x : range - x - 1
+                    "selp.u32 %3, %8, %7, pb;\n\t"        // P of the chosen child
+                    "mul.hi.u32 %2, %1, %3;\n\t"          // product for the next step
+                    "@!pb add.u32 %0, mid, 1;\n\t"        // bit 0: low = mid + 1
+                    "selp.u32 %4, 1, 0, pb;\n\t"
+                    "add.u32 hi, %0, %1;\n\t"
+                    "xor.b32 t, %0, hi;\n\t"
+                    "min.u32 %5, %5, t;\n\t"
+                    "}"
+                    : "+r"(flow), "+r"(frange), "+r"(x), "+r"(pcur), "=r"(bit), "+r"(tmin)
+                    : "r"(code), "r"(kid0), "r"(kid1));
+                node = node * 2 + bit;
+                kid0 = bit ? gk.z : gk.x;
+                kid1 = bit ? gk.w : gk.y;
+                if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
+            }
+            if (tmin >= (1u << 24)) {
+                low = flow;
+                range = frange;
+            } else {
+                // exact tier: the reference loop, probabilities fetched per step
+                node = 1;
                 u32 high = low + range;
-                while ((low ^ high) < (1u << 24)) {
-                    low <<= 8;
-                    high = (high << 8) | 0xFFu;
-                    const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;
-                    ip += (ip < insize);
-                    code = (code << 8) + add;
+                for (int k = 0; k < 8; k++) {
+                    const u32 mid = low + __umulhi(high - low, pt[node]);
+                    const bool bit = code <= mid;
+                    if (bit) high = mid; else low = mid + 1u;
+                    node = node * 2 + (bit ? 1u : 0u);
+                    while ((low ^ high) < (1u << 24)) {
+                        low <<= 8;
+                        high = (high << 8) | 0xFFu;
+                        const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;
+                        ip += (ip < insize);
+                        code = (code << 8) + add;
+                    }
                 }
                 range = high - low;
-                x = mulhi_pinned(range, pcur);
             }
         }
         const u32 byte = node & 255u;
@@ -534,7 +522,6 @@ inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
-    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     return cudaSuccess;
 }
