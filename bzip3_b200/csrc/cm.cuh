@@ -172,7 +172,13 @@ __global__ void __launch_bounds__(kCmThreads) cm_decode_single_kernel(const u8* 
     if (threadIdx.x == 0) cm_decode_serial(cm_tables_at(cm_smem), in, insize, out, n);
 }
 
-// ---- chunked two-warp encoder -----------------------------------------------------------------
+// branch-free counter update: bit ? v + ((v ^ 65535) >> rate) : v - (v >> rate)
+BZ_D u32 cm_adapt_bf(u32 v, u32 ones /* bit ? 0xFFFF : 0 */, int rate) {
+    const u32 u = (v ^ ones) >> rate;
+    return ones ? v + u : v - u;
+}
+
+// ---- chunked pipelined encoder -----------------------------------------------------------------
 // Warp 0 runs the model: lane d (0..7) owns tree depth d, i.e. bit position d of every byte.  A node
 // of depth d is only ever coded at bit position d, so the eight lanes touch disjoint counters and
 // need no synchronisation with each other.  For a chunk of 1024 bytes they leave 8192 entries
@@ -183,9 +189,9 @@ __global__ void __launch_bounds__(kCmThreads) cm_decode_single_kernel(const u8* 
 //     bit 1: range = x            bit 0: low += x + 1, range -= x + 1
 // The top bytes of low and low+range can only agree when range < 2^24, which is the cheap test on
 // the critical path; the exact test and the byte output live in the rare slow path.
-constexpr int kCmEncChunk = 1024;
-constexpr int kCmEncThreads = 64;
-constexpr size_t kCmEncSmemBytes = (size_t)kCmTableU16 * 2 + 2 * (size_t)kCmEncChunk * 8 * 4 + 2 * (size_t)kCmEncChunk + 64;
+constexpr int kCmEncChunk = 768;
+constexpr int kCmEncThreads = 96;
+constexpr size_t kCmEncSmemBytes = (size_t)kCmTableU16 * 2 + 2 * (size_t)kCmEncChunk * 8 * 4 + 2 * (size_t)kCmEncChunk * 8 * 2 + 3 * (size_t)kCmEncChunk + 64;
 
 // mul.hi that the compiler may neither sink into a branch nor drop: it is issued speculatively for the
 // NEXT decision before the (rare) renormalisation test of the current one has resolved, which takes the
@@ -240,79 +246,124 @@ __device__ __noinline__ uint4 rc_exact_byte(u32 low, u32 range, s32 op, u32 sym,
     return make_uint4(low, high - low, (u32)op, 0u);
 }
 
+// Three-stage chunk pipeline (one __syncthreads per chunk, no polling):
+//   warp 0, lanes 0..7  stage 1: c0 / c1 counters of tree depth `lane`  -> mixed probability p (16 bit)
+//   warp 2, lanes 0..7  stage 2: SSE rows c2 of depth `lane`            -> P << 14
+//   warp 1, lane 0      stage 3: range coder
+// Stage s works on chunk it-s in iteration `it`.  A node of depth d is only ever coded at bit position d,
+// so the eight lanes of a stage own disjoint counters and never synchronise with each other.
 template <int MODE>
 __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const u8* __restrict__ in, s32 n,
                                                                          u8* __restrict__ out, s32* out_size) {
     extern __shared__ __align__(16) u16 cm_smem[];
-    u32* pbuf = reinterpret_cast<u32*>(cm_smem + kCmTableU16);           // [2][kCmEncChunk * 8]  P << 14
-    u8* sbytes = reinterpret_cast<u8*>(pbuf + 2 * kCmEncChunk * 8);      // [2][kCmEncChunk]
+    u32* pbuf = reinterpret_cast<u32*>(cm_smem + kCmTableU16);                 // [2][chunk * 8]  P << 14
+    u16* pmid = reinterpret_cast<u16*>(pbuf + 2 * kCmEncChunk * 8);            // [2][chunk * 8]  p
+    u8* sbytes = reinterpret_cast<u8*>(pmid + 2 * kCmEncChunk * 8);            // [3][chunk]
     cm_tables_init_smem(cm_smem);
     __syncthreads();
     const u32 lane = lane_id();
     const u32 warp = warp_id();
     const s32 nchunks = (n + kCmEncChunk - 1) / kCmEncChunk;
-    const CmTables t = cm_tables_at(cm_smem);
-    CmCtx c{0, 0, 0, 0u};
+    u16* const c0 = cm_smem;
+    u16* const c1 = cm_smem + kCmC0;
+    u16* const c2 = cm_smem + kCmC0 + kCmC1;
+    const int sh_node = 8 - (int)lane, sh_bit = 7 - (int)lane, top = 1 << lane;
+    int prev1 = 0, prev2 = 0;   // stage-private copies of the byte context
+    u32 run = 0;
     u32 low = 0, range = 0xFFFFFFFFu;
     s32 op = 0;
-    for (s32 it = 0; it <= nchunks; it++) {
-        if (warp == 0 && it < nchunks) {
-            const s32 base = it * kCmEncChunk;
-            const s32 len = (n - base) < kCmEncChunk ? (n - base) : kCmEncChunk;
-            u8* sb = sbytes + (it & 1) * kCmEncChunk;
-            for (s32 k = lane; k < len; k += 32) sb[k] = in[base + k];
-            __syncwarp();
-            if (lane < 8) {
-                u32* pb = pbuf + (it & 1) * (kCmEncChunk * 8) + lane;
-                const int sh_node = 8 - (int)lane, sh_bit = 7 - (int)lane, top = 1 << lane;
-                for (s32 k = 0; k < len; k++) {
-                    const int sym = sb[k];
-                    cm_ctx_begin_byte(c);
-                    const int node = top | (sym >> sh_node);
-                    const int bit = (sym >> sh_bit) & 1;
-                    pb[k * 8] = cm_code_known_bit(t, node, c, bit) << 14;
-                    cm_ctx_end_byte(c, sym);
+    for (s32 it = 0; it < nchunks + 2; it++) {
+        if (warp == 0) {
+            if (it < nchunks) {
+                const s32 base = it * kCmEncChunk;
+                const s32 len = (n - base) < kCmEncChunk ? (n - base) : kCmEncChunk;
+                u8* sb = sbytes + (it % 3) * kCmEncChunk;
+                for (s32 k = lane; k < len; k += 32) sb[k] = in[base + k];
+                __syncwarp();
+                if (lane < 8) {
+                    u16* pm = pmid + (it & 1) * (kCmEncChunk * 8) + lane;
+                    for (s32 k = 0; k < len; k++) {
+                        const int sym = sb[k];
+                        const int node = top | (sym >> sh_node);
+                        const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
+                        u16* q0 = c0 + node;
+                        u16* q1 = c1 + prev1 * 256 + node;
+                        const int a = *q0, b = *q1, d = c1[prev2 * 256 + node];
+                        pm[k * 8] = (u16)(((a + b) * 7 + d + d) >> 4);
+                        *q0 = (u16)cm_adapt_bf((u32)a, ones, 2);
+                        *q1 = (u16)cm_adapt_bf((u32)b, ones, 4);
+                        prev2 = prev1;
+                        prev1 = sym;
+                    }
                 }
             }
-        } else if (warp == 1 && lane == 0 && it > 0) {
-            const s32 base = (it - 1) * kCmEncChunk;
-            const s32 len = (n - base) < kCmEncChunk ? (n - base) : kCmEncChunk;
-            const u32* pw = pbuf + ((it - 1) & 1) * (kCmEncChunk * 8);
-            const uint4* pv = reinterpret_cast<const uint4*>(pw);
-            const u8* sb = sbytes + ((it - 1) & 1) * kCmEncChunk;
-            uint4 a = pv[0], b = pv[1];
-            u32 sym = sb[0];
-            u32 x = mulhi_pinned(range, a.x);
-            for (s32 k = 0; k < len; k++) {
-                const uint4 ca = a, cb = b;
-                const u32 cs = sym;
-                const s32 kn = (k + 1 < len) ? k + 1 : k;  // the last byte re-reads itself; its look-ahead product is unused
-                a = pv[2 * kn];
-                b = pv[2 * kn + 1];
-                sym = sb[kn];
-                if (MODE == 0) {
-                    const u32 low0 = low, range0 = range;
-                    u32 tmin = 0xFFFFFFFFu;
-                    rc_fast_step(low, range, x, tmin, cs & 0x80u, ca.y);
-                    rc_fast_step(low, range, x, tmin, cs & 0x40u, ca.z);
-                    rc_fast_step(low, range, x, tmin, cs & 0x20u, ca.w);
-                    rc_fast_step(low, range, x, tmin, cs & 0x10u, cb.x);
-                    rc_fast_step(low, range, x, tmin, cs & 0x08u, cb.y);
-                    rc_fast_step(low, range, x, tmin, cs & 0x04u, cb.z);
-                    rc_fast_step(low, range, x, tmin, cs & 0x02u, cb.w);
-                    rc_fast_step(low, range, x, tmin, cs & 0x01u, a.x);
-                    if (tmin < (1u << 24)) {  // some decision needed a shift: redo this byte exactly
-                        const uint4 r = rc_exact_byte(low0, range0, op, cs, pw + 8 * k, out);
+        } else if (warp == 2) {
+            if (lane < 8 && it >= 1 && it - 1 < nchunks) {
+                const s32 ch = it - 1;
+                const s32 base = ch * kCmEncChunk;
+                const s32 len = (n - base) < kCmEncChunk ? (n - base) : kCmEncChunk;
+                const u8* sb = sbytes + (ch % 3) * kCmEncChunk;
+                const u16* pm = pmid + (ch & 1) * (kCmEncChunk * 8) + lane;
+                u32* pb = pbuf + (ch & 1) * (kCmEncChunk * 8) + lane;
+                for (s32 k = 0; k < len; k++) {
+                    const int sym = sb[k];
+                    const int p = pm[k * 8];
+                    run = (prev1 == prev2) ? run + 1 : 0;           // run flag of this byte (src/libbz3.c:367-372)
+                    const int flag = run > 2;
+                    const int node = top | (sym >> sh_node);
+                    const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
+                    u16* cell = c2 + (2 * node + flag) * 17 + (p >> 12);
+                    const int lo = cell[0], hi = cell[1];
+                    const int sse = lo + (((hi - lo) * (p & 4095)) >> 12);
+                    pb[k * 8] = (u32)(sse * 3 + p) << 14;
+                    cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
+                    cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
+                    prev2 = prev1;
+                    prev1 = sym;
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0 && it >= 2) {
+                const s32 ch = it - 2;
+                const s32 base = ch * kCmEncChunk;
+                const s32 len = (n - base) < kCmEncChunk ? (n - base) : kCmEncChunk;
+                const u32* pw = pbuf + (ch & 1) * (kCmEncChunk * 8);
+                const uint4* pv = reinterpret_cast<const uint4*>(pw);
+                const u8* sb = sbytes + (ch % 3) * kCmEncChunk;
+                uint4 a = pv[0], b = pv[1];
+                u32 sym = sb[0];
+                u32 x = mulhi_pinned(range, a.x);
+                for (s32 k = 0; k < len; k++) {
+                    const uint4 ca = a, cb = b;
+                    const u32 cs = sym;
+                    const s32 kn = (k + 1 < len) ? k + 1 : k;  // the last byte re-reads itself; that product is unused
+                    a = pv[2 * kn];
+                    b = pv[2 * kn + 1];
+                    sym = sb[kn];
+                    if (MODE == 0) {
+                        const u32 low0 = low, range0 = range;
+                        u32 tmin = 0xFFFFFFFFu;
+                        rc_fast_step(low, range, x, tmin, cs & 0x80u, ca.y);
+                        rc_fast_step(low, range, x, tmin, cs & 0x40u, ca.z);
+                        rc_fast_step(low, range, x, tmin, cs & 0x20u, ca.w);
+                        rc_fast_step(low, range, x, tmin, cs & 0x10u, cb.x);
+                        rc_fast_step(low, range, x, tmin, cs & 0x08u, cb.y);
+                        rc_fast_step(low, range, x, tmin, cs & 0x04u, cb.z);
+                        rc_fast_step(low, range, x, tmin, cs & 0x02u, cb.w);
+                        rc_fast_step(low, range, x, tmin, cs & 0x01u, a.x);
+                        if (tmin < (1u << 24)) {  // some decision needed a shift: redo this byte exactly
+                            const uint4 r = rc_exact_byte(low0, range0, op, cs, pw + 8 * k, out);
+                            low = r.x;
+                            range = r.y;
+                            op = (s32)r.z;
+                            x = mulhi_pinned(range, a.x);
+                        }
+                    } else {
+                        const uint4 r = rc_exact_byte(low, range, op, cs, pw + 8 * k, out);
                         low = r.x;
                         range = r.y;
                         op = (s32)r.z;
-                        x = mulhi_pinned(range, a.x);
                     }
-                } else {
-                    const uint4 r = rc_exact_byte(low, range, op, cs, pw + 8 * k, out);
-                    low = r.x;
-                    range = r.y;
-                    op = (s32)r.z;
                 }
             }
         }
@@ -330,65 +381,72 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
 // ---- tree-parallel decoder ---------------------------------------------------------------------
 // Decoding is one dependent chain: the next context depends on the bit just decoded.  What does not
 // depend on the bits of the current byte is the probability of every one of the 255 tree nodes (no node
-// is visited twice within a byte, and prev1/prev2/runflag are fixed at the byte boundary).  So, per byte:
-//   A  128 threads compute P for all 255 nodes (thread t owns nodes t and t+128 and is the only
-//      thread that ever reads or writes their counters)                       -> ptab[node]
-//   B  every thread walks the same 8-step chain down the tree, fetching the two child probabilities
-//      of the next node one step ahead (no table lookups or model arithmetic left on the chain)
-//   C  the 8 owners of the visited nodes update their counters from registers.
-// One __syncthreads per byte (ptab is double buffered).  The compressed bytes are staged through a
-// 2 KiB shared window so the renormalisation never waits on global memory.
-constexpr int kCmDecThreads = 128;
-constexpr size_t kCmDecSmemBytes = (size_t)kCmTableU16 * 2 + 2 * 256 * 4 + 2048 + 64;
-
-struct NodeCalc {
-    int a, b, lo, hi;
-    u16* q1;
-    u16* row;
-};
-BZ_D u32 cm_node_predict(const CmTables& t, int node, int prev1, int prev2, int flag, NodeCalc& k) {
-    k.q1 = t.c1 + prev1 * 256 + node;
-    k.a = t.c0[node];
-    k.b = *k.q1;
-    const int d = t.c1[prev2 * 256 + node];
-    const int p = ((k.a + k.b) * 7 + d + d) >> 4;
-    k.row = t.c2 + (2 * node + flag) * 17 + (p >> 12);
-    k.lo = k.row[0];
-    k.hi = k.row[1];
-    const int sse = k.lo + (((k.hi - k.lo) * (p & 4095)) >> 12);
-    return (u32)(sse * 3 + p);
-}
-BZ_D void cm_node_learn(const CmTables& t, int node, const NodeCalc& k, int bit) {
-    t.c0[node] = (u16)cm_adapt((u32)k.a, bit, 2);
-    *k.q1 = (u16)cm_adapt((u32)k.b, bit, 4);
-    k.row[0] = (u16)cm_adapt((u32)k.lo, bit, 6);
-    k.row[1] = (u16)cm_adapt((u32)k.hi, bit, 6);
-}
-
-// branch-free counter update: bit ? v + ((v ^ 65535) >> rate) : v - (v >> rate)
-BZ_D u32 cm_adapt_bf(u32 v, u32 ones /* bit ? 0xFFFF : 0 */, int rate) {
-    const u32 u = (v ^ ones) >> rate;
-    return ones ? v + u : v - u;
-}
+// is visited twice within a byte, and prev1/prev2/runflag are fixed at the byte boundary).  Roles:
+//   warps 1..8  256 model threads, thread owns ONE node and is the only one that ever touches its
+//               counters: (C) learn the previous byte if the node was on its path, (A) predict -> ptab
+//   warp 0      the chain: walks the 8 levels using ptab, two-tier like the encoder (branch-free fast
+//               byte, exact redo when a renormalisation was needed), publishes the byte.
+// Two __syncthreads per byte (ptab ready / byte ready).  The compressed bytes are staged through a
+// 2 KiB shared window owned by warp 0, so the renormalisation never waits on global memory.
+constexpr int kCmDecThreads = 288;
+constexpr size_t kCmDecSmemBytes = (size_t)kCmTableU16 * 2 + 256 * 4 + 2048 + 64;
 
 __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8* __restrict__ in, s32 insize,
                                                                       u8* __restrict__ out, s32 n) {
     extern __shared__ __align__(16) u16 cm_smem[];
-    u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [2][256]
-    u8* scode = reinterpret_cast<u8*>(ptab + 512);              // [2048] window of the compressed stream
+    u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [256]  P << 14 per node
+    u8* scode = reinterpret_cast<u8*>(ptab + 256);              // [2048] window of the compressed stream
+    volatile u32* vbyte = reinterpret_cast<volatile u32*>(scode + 2048);  // last decoded byte
     cm_tables_init_smem(cm_smem);
     const int tid = threadIdx.x;
-    for (int k = tid; k < 2048; k += kCmDecThreads) scode[k] = (k < insize) ? in[k] : 0;
+    if (tid < 32)
+        for (int k = tid; k < 2048; k += 32) scode[k] = (k < insize) ? in[k] : 0;
     __syncthreads();
-    // thread `tid` owns nodes tid (depth 0..6, tid >= 1) and tid + 128 (depth 7)
-    const int nodeA = tid, nodeB = tid + 128;
-    const int shA = tid ? 8 - (31 - __clz(tid)) : 8;      // (256|byte) >> shA == nodeA  <=> nodeA is on the path
-    u16* const c0A = cm_smem + nodeA;
-    u16* const c0B = cm_smem + nodeB;
-    u16* const c1A = cm_smem + kCmC0 + nodeA;             // + prev * 256
-    u16* const c1B = cm_smem + kCmC0 + nodeB;
-    u16* const rowA = cm_smem + kCmC0 + kCmC1 + (2 * nodeA) * 17;   // + flag * 17 + cell
-    u16* const rowB = cm_smem + kCmC0 + kCmC1 + (2 * nodeB) * 17;
+    if (tid >= 32) {
+        // ------------------------------------------------------------------ model thread
+        const int node = tid - 32;                                        // 0 is a dummy
+        const int sh = node ? 8 - (31 - __clz(node)) : 8;                 // (256|byte) >> sh == node <=> on the path
+        u16* const q0 = cm_smem + node;
+        u16* const c1col = cm_smem + kCmC0 + node;                        // + prev * 256
+        u16* const rows = cm_smem + kCmC0 + kCmC1 + (2 * node) * 17;      // + flag * 17 + cell
+        int prev1 = 0, prev2 = 0;
+        u32 run = 0;
+        int a = 0, b = 0, lo = 0, hi = 0;
+        u16* q1 = c1col;
+        u16* cell = rows;
+        for (s32 i = 0; i < n; i++) {
+            if (i > 0) {
+                const u32 byte = *vbyte;
+                // (C) learn byte i-1
+                if (node != 0 && ((256u | byte) >> sh) == (u32)node) {
+                    const u32 ones = ((byte >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
+                    *q0 = (u16)cm_adapt_bf((u32)a, ones, 2);
+                    *q1 = (u16)cm_adapt_bf((u32)b, ones, 4);
+                    cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
+                    cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
+                }
+                prev2 = prev1;
+                prev1 = (int)byte;
+            }
+            run = (prev1 == prev2) ? run + 1 : 0;
+            const int flag = run > 2;
+            // (A) predict byte i
+            q1 = c1col + prev1 * 256;
+            a = *q0;
+            b = *q1;
+            const int d = c1col[prev2 * 256];
+            const int p = ((a + b) * 7 + d + d) >> 4;
+            cell = rows + flag * 17 + (p >> 12);
+            lo = cell[0];
+            hi = cell[1];
+            const int sse = lo + (((hi - lo) * (p & 4095)) >> 12);
+            ptab[node] = (u32)(sse * 3 + p) << 14;   // slot 0 is never read
+            __syncthreads();   // ptab ready
+            __syncthreads();   // byte ready
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- chain warp (all lanes identical)
     s32 wlo = 0;  // the window holds stream bytes [wlo, wlo + 2048)
     s32 ip = 0;
     u32 low = 0, range = 0xFFFFFFFFu, code = 0;
@@ -398,31 +456,9 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         ip += (ip < insize);
         code = (code << 8) + add;
     }
-    int prev1 = 0, prev2 = 0;
-    u32 run = 0;
+    const u32* pt = ptab;
     for (s32 i = 0; i < n; i++) {
-        run = (prev1 == prev2) ? run + 1 : 0;
-        const int flag = run > 2;
-        u32* pt = ptab + (i & 1) * 256;
-        // ---- A: probabilities of both owned nodes (the two chains interleave)
-        u16* const q1A = c1A + prev1 * 256;
-        u16* const q1B = c1B + prev1 * 256;
-        const int aA = *c0A, aB = *c0B;
-        const int bA = *q1A, bB = *q1B;
-        const int dA = c1A[prev2 * 256], dB = c1B[prev2 * 256];
-        const int pA = ((aA + bA) * 7 + dA + dA) >> 4;
-        const int pB = ((aB + bB) * 7 + dB + dB) >> 4;
-        u16* const cellA = rowA + flag * 17 + (pA >> 12);
-        u16* const cellB = rowB + flag * 17 + (pB >> 12);
-        const int loA = cellA[0], hiA = cellA[1];
-        const int loB = cellB[0], hiB = cellB[1];
-        const int sseA = loA + (((hiA - loA) * (pA & 4095)) >> 12);
-        const int sseB = loB + (((hiB - loB) * (pB & 4095)) >> 12);
-        pt[nodeA] = (u32)(sseA * 3 + pA) << 14;   // slot 0 is never read
-        pt[nodeB] = (u32)(sseB * 3 + pB) << 14;
-        __syncthreads();
-        // ---- B: the serial chain, identical in every thread.  pcur = P(node), kids = P(children of node),
-        //         gk = P(grandchildren of node); the 4 grandchildren are one aligned 128-bit row of ptab.
+        __syncthreads();   // ptab ready
         const uint4 g0 = *reinterpret_cast<const uint4*>(pt);
         uint4 gk = *reinterpret_cast<const uint4*>(pt + 4);
         u32 node = 1;
@@ -483,37 +519,20 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
             }
         }
         const u32 byte = node & 255u;
-        // ---- C: owners of the visited nodes learn (branch-free arithmetic, predicated stores)
-        {
-            const bool onA = tid != 0 && ((256u | byte) >> shA) == (u32)nodeA;
-            const u32 onesA = ((byte >> (shA - 1)) & 1u) ? 0xFFFFu : 0u;
-            if (onA) {
-                *c0A = (u16)cm_adapt_bf((u32)aA, onesA, 2);
-                *q1A = (u16)cm_adapt_bf((u32)bA, onesA, 4);
-                cellA[0] = (u16)cm_adapt_bf((u32)loA, onesA, 6);
-                cellA[1] = (u16)cm_adapt_bf((u32)hiA, onesA, 6);
-            }
-            const bool onB = (128u | (byte >> 1)) == (u32)nodeB;
-            const u32 onesB = (byte & 1u) ? 0xFFFFu : 0u;
-            if (onB) {
-                *c0B = (u16)cm_adapt_bf((u32)aB, onesB, 2);
-                *q1B = (u16)cm_adapt_bf((u32)bB, onesB, 4);
-                cellB[0] = (u16)cm_adapt_bf((u32)loB, onesB, 6);
-                cellB[1] = (u16)cm_adapt_bf((u32)hiB, onesB, 6);
-            }
+        if (tid == 0) {
+            *vbyte = byte;
+            out[i] = (u8)byte;
         }
-        if (tid == 0) out[i] = (u8)byte;
-        prev2 = prev1;
-        prev1 = (int)byte;
-        if (ip - wlo >= 1024) {  // uniform: every thread follows the same chain
-            __syncthreads();
-            for (int k = tid; k < 1024; k += kCmDecThreads) {
+        if (ip - wlo >= 1024) {  // uniform in the warp; the window belongs to this warp alone
+            __syncwarp();
+            for (int k = tid; k < 1024; k += 32) {
                 const s32 src = wlo + 2048 + k;
                 scode[src & 2047] = (src < insize) ? in[src] : 0;
             }
             wlo += 1024;
-            __syncthreads();
+            __syncwarp();
         }
+        __syncthreads();   // byte ready
     }
 }
 
