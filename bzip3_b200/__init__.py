@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbzip3_b200.so")
+LIB_PATH = os.environ.get("BZ3_B200_LIB") or os.path.join(_HERE, "libbzip3_b200.so")  # env override: tuning builds
 
 BZ3_OK = 0
 BZ3_ERR_OUT_OF_BOUNDS = -1

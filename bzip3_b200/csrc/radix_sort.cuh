@@ -22,9 +22,15 @@ constexpr int kRsWarps = kRsThreads / 32;
 
 template <typename K>
 struct RsCfg;
+#ifndef BZ_RS_ITEMS_U64
+#define BZ_RS_ITEMS_U64 16
+#endif
+#ifndef BZ_RS_MIN_BLOCKS
+#define BZ_RS_MIN_BLOCKS 3
+#endif
 template <>
 struct RsCfg<u64> {
-    static constexpr int kItems = 16;
+    static constexpr int kItems = BZ_RS_ITEMS_U64;
 };
 template <>
 struct RsCfg<u32> {
@@ -75,7 +81,7 @@ rs_tile_hist_kernel(const K* __restrict__ keys, u32 n, int shift, u32 mask, u32*
 
 // KOUT: write keys;  VOUT: write values.  ValGen produces the value of input record i.
 template <typename K, bool KOUT, bool VOUT, typename ValGen>
-__global__ void __launch_bounds__(kRsThreads)
+__global__ void __launch_bounds__(kRsThreads, BZ_RS_MIN_BLOCKS)
 rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, u32* __restrict__ vout, u32 n,
                   int shift, u32 mask, const u32* __restrict__ bases, u32 ntiles) {
     constexpr int ITEMS = RsCfg<K>::kItems;
@@ -94,14 +100,22 @@ rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, 
     __syncthreads();
 
     K key[ITEMS];
+    u32 val[VOUT ? ITEMS : 1];
     u16 rank[ITEMS];
     const u32 base = tile_base + w * (32 * ITEMS);
     const u32 lt = lanemask_lt();
+    // all loads of the tile are issued before anything consumes them (memory-level parallelism: the
+    // v0 profile showed 60 % long-scoreboard stalls with the value loads serialised behind shared stores)
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        u32 i = base + it * 32 + l;
+        key[it] = (i < n) ? kin[i] : (K)0;
+        if (VOUT) val[it] = (i < n) ? vgen(i) : 0u;
+    }
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
         u32 i = base + it * 32 + l;
         bool valid = i < n;
-        key[it] = valid ? kin[i] : (K)0;
         // records past n get digit 255; they are last in tile order, so their stable rank puts them
         // behind every real record and the write-out loop (j < count) never emits them
         u32 d = valid ? rs_digit(key[it], shift, mask) : 255u;
@@ -150,7 +164,7 @@ rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, 
         u32 pos = lbase[d] + warp_cnt[w * 256 + d] + rank[it];
         if (pos < TILE) {
             if (KOUT) skeys[pos] = key[it];
-            if (VOUT) svals[pos] = (i < n) ? vgen(i) : 0u;
+            if (VOUT) svals[pos] = val[it];
             if (!KOUT) reinterpret_cast<u8*>(skeys)[pos] = (u8)d;  // digit is still needed for the write-out
         }
     }
