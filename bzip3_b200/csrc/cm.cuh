@@ -231,7 +231,38 @@ BZ_D void rc_fast_step(u32& low, u32& range, u32& x, u32& tmin, u32 bit, u32 mne
         : "r"(bit), "r"(mnext));
 }
 
-// exact tier: the reference recurrence for the 8 decisions of one byte; m = the byte's 8 multipliers
+// exact tier, one decision: same recurrence, then the renormalisation of the reference.  range < 2^24 is
+// necessary for the top bytes of low and low+range to agree, so that cheap test guards the loop.
+BZ_D void rc_exact_step(u32& low, u32& range, u32& x, s32& op, u32 bit, u32 mnext, u8* __restrict__ out) {
+    u32 slow;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pb, ps;\n\t"
+        ".reg .u32 nx;\n\t"
+        "setp.ne.u32 pb, %4, 0;\n\t"
+        "not.b32 nx, %2;\n\t"
+        "@pb mov.u32 %1, %2;\n\t"
+        "@!pb add.u32 %1, %1, nx;\n\t"
+        "mul.hi.u32 %2, %1, %5;\n\t"
+        "@!pb sub.u32 %0, %0, nx;\n\t"
+        "setp.lt.u32 ps, %1, 0x1000000;\n\t"
+        "selp.u32 %3, 1, 0, ps;\n\t"
+        "}"
+        : "+r"(low), "+r"(range), "+r"(x), "=r"(slow)
+        : "r"(bit), "r"(mnext));
+    if (slow) {
+        u32 high = low + range;
+        while ((low ^ high) < (1u << 24)) {
+            out[op++] = (u8)(low >> 24);
+            low <<= 8;
+            high = (high << 8) | 0xFFu;
+        }
+        range = high - low;
+        x = mulhi_pinned(range, mnext);
+    }
+}
+
+// exact tier, whole byte from memory (cross-check variant only)
 __device__ __noinline__ uint4 rc_exact_byte(u32 low, u32 range, s32 op, u32 sym, const u32* m, u8* out) {
     u32 high = low + range;
     for (int j = 0; j < 8; j++) {
@@ -341,7 +372,7 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                     b = pv[2 * kn + 1];
                     sym = sb[kn];
                     if (MODE == 0) {
-                        const u32 low0 = low, range0 = range;
+                        const u32 low0 = low, range0 = range, x0 = x;
                         u32 tmin = 0xFFFFFFFFu;
                         rc_fast_step(low, range, x, tmin, cs & 0x80u, ca.y);
                         rc_fast_step(low, range, x, tmin, cs & 0x40u, ca.z);
@@ -352,11 +383,17 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                         rc_fast_step(low, range, x, tmin, cs & 0x02u, cb.w);
                         rc_fast_step(low, range, x, tmin, cs & 0x01u, a.x);
                         if (tmin < (1u << 24)) {  // some decision needed a shift: redo this byte exactly
-                            const uint4 r = rc_exact_byte(low0, range0, op, cs, pw + 8 * k, out);
-                            low = r.x;
-                            range = r.y;
-                            op = (s32)r.z;
-                            x = mulhi_pinned(range, a.x);
+                            low = low0;
+                            range = range0;
+                            x = x0;
+                            rc_exact_step(low, range, x, op, cs & 0x80u, ca.y, out);
+                            rc_exact_step(low, range, x, op, cs & 0x40u, ca.z, out);
+                            rc_exact_step(low, range, x, op, cs & 0x20u, ca.w, out);
+                            rc_exact_step(low, range, x, op, cs & 0x10u, cb.x, out);
+                            rc_exact_step(low, range, x, op, cs & 0x08u, cb.y, out);
+                            rc_exact_step(low, range, x, op, cs & 0x04u, cb.z, out);
+                            rc_exact_step(low, range, x, op, cs & 0x02u, cb.w, out);
+                            rc_exact_step(low, range, x, op, cs & 0x01u, a.x, out);
                         }
                     } else {
                         const uint4 r = rc_exact_byte(low, range, op, cs, pw + 8 * k, out);
@@ -499,23 +536,51 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
                 low = flow;
                 range = frange;
             } else {
-                // exact tier: the reference loop, probabilities fetched per step
+                // exact tier: same walk, renormalising after every step like the reference
                 node = 1;
-                u32 high = low + range;
+                gk = *reinterpret_cast<const uint4*>(pt + 4);
+                pcur = g0.y;
+                kid0 = g0.z;
+                kid1 = g0.w;
+                x = mulhi_pinned(range, pcur);
+#pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const u32 mid = low + __umulhi(high - low, pt[node]);
-                    const bool bit = code <= mid;
-                    if (bit) high = mid; else low = mid + 1u;
-                    node = node * 2 + (bit ? 1u : 0u);
-                    while ((low ^ high) < (1u << 24)) {
-                        low <<= 8;
-                        high = (high << 8) | 0xFFu;
-                        const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;
-                        ip += (ip < insize);
-                        code = (code << 8) + add;
+                    u32 bit, slow;
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred pb, ps;\n\t"
+                        ".reg .u32 mid, nx, r0;\n\t"
+                        "add.u32 mid, %0, %2;\n\t"
+                        "not.b32 nx, %2;\n\t"
+                        "setp.le.u32 pb, %6, mid;\n\t"
+                        "add.u32 r0, %1, nx;\n\t"
+                        "selp.u32 %1, %2, r0, pb;\n\t"
+                        "selp.u32 %3, %8, %7, pb;\n\t"
+                        "mul.hi.u32 %2, %1, %3;\n\t"
+                        "@!pb add.u32 %0, mid, 1;\n\t"
+                        "selp.u32 %4, 1, 0, pb;\n\t"
+                        "setp.lt.u32 ps, %1, 0x1000000;\n\t"
+                        "selp.u32 %5, 1, 0, ps;\n\t"
+                        "}"
+                        : "+r"(low), "+r"(range), "+r"(x), "+r"(pcur), "=r"(bit), "=r"(slow)
+                        : "r"(code), "r"(kid0), "r"(kid1));
+                    node = node * 2 + bit;
+                    kid0 = bit ? gk.z : gk.x;
+                    kid1 = bit ? gk.w : gk.y;
+                    if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
+                    if (slow) {
+                        u32 high = low + range;
+                        while ((low ^ high) < (1u << 24)) {
+                            low <<= 8;
+                            high = (high << 8) | 0xFFu;
+                            const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;
+                            ip += (ip < insize);
+                            code = (code << 8) + add;
+                        }
+                        range = high - low;
+                        x = mulhi_pinned(range, pcur);
                     }
                 }
-                range = high - low;
             }
         }
         const u32 byte = node & 255u;

@@ -23,7 +23,7 @@ constexpr int kRsWarps = kRsThreads / 32;
 template <typename K>
 struct RsCfg;
 #ifndef BZ_RS_ITEMS_U64
-#define BZ_RS_ITEMS_U64 16
+#define BZ_RS_ITEMS_U64 12
 #endif
 #ifndef BZ_RS_MIN_BLOCKS
 #define BZ_RS_MIN_BLOCKS 3
