@@ -28,6 +28,12 @@ def main():
         out = np.zeros(bzip3_b200.bound(n) + 64, np.uint8)
         back = np.zeros(bzip3_b200.bound(n) + 64, np.uint8)
         pi, po, pb = (a.ctypes.data_as(u8p) for a in (data, out, back))
+        if stage.endswith("_bwt"):  # entropy stage on BWT output (what it sees inside a block)
+            tmp = np.zeros(n + 64, np.uint8)
+            L.bz3_b200_stage_bwt(s.handle, pi, n, tmp.ctypes.data_as(u8p))
+            data = tmp[:n].copy()
+            pi = data.ctypes.data_as(u8p)
+            stage = stage[:-4]
         for r in range(rep):
             t0 = time.perf_counter()
             if stage == "bwt":
