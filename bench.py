@@ -18,6 +18,13 @@ Launch: python bench.py [--gpus N --steps K --warmup W]  or, for N>1,
 """
 from __future__ import annotations
 
+import os as _os
+
+# One CUDA stream per block: give every stream its own hardware queue, otherwise a copy queued behind one
+# block's seconds-long coder kernel falsely serialises the other blocks' short kernels (must be set before
+# the CUDA context exists).
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import argparse
 import ctypes as C
 import json

@@ -24,6 +24,11 @@
 
 using namespace bz3;
 
+// One stream per block: ask for enough hardware queues that streams do not alias (the default of 8 lets a
+// copy queued behind one block's long coder kernel stall other blocks' launches).  Only effective when the
+// library is loaded before the CUDA context is created; never overrides the user's setting.
+__attribute__((constructor)) static void bz3_b200_env_defaults() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 #ifndef BZ3_VERSION_STRING
 #define BZ3_VERSION_STRING "1.5.2-b200"
 #endif
