@@ -82,6 +82,7 @@ struct bz3_state {
     s32 sort_rounds;
     double sort_ms;
     int variant[BZ3_STAGE_COUNT];
+    cudaEvent_t sort_ev[2 * 40];
 };
 
 namespace {
@@ -219,11 +220,19 @@ cudaError_t run_bwt(bz3_state* s, u8* d_in, u32 n, u8* d_out, s32* idx) {
     SufsortBuffers B;
     if (!carve_sufsort(s, n, B)) return cudaErrorMemoryAllocation;
     BZ_CUDA_TRY(cudaMemsetAsync(d_in + n, 0, 16, s->stream));  // zero padding read by the 7-byte key kernel
-    int rounds = 0;
+    int rounds = 0, nev = 0;
     u64 rp = 0;
+    B.ev = s->sort_ev;
+    B.max_ev = 40;
+    B.used_ev = &nev;
     cudaError_t e = suffix_bwt(s->stream, d_in, n, d_out, B, idx, &rounds, &rp);
     s->sort_rounds = rounds;
     s->sort_records += rp;
+    if (e == cudaSuccess && cudaStreamSynchronize(s->stream) == cudaSuccess)
+        for (int k = 0; k < nev; k++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, s->sort_ev[2 * k], s->sort_ev[2 * k + 1]) == cudaSuccess) s->sort_ms += ms;
+        }
     return e;
 }
 
@@ -482,6 +491,7 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     }
     for (int i = 0; i < BZ3_STAGE_COUNT && ok; i++)
         ok = cudaEventCreate(&s->clk.a[i]) == cudaSuccess && cudaEventCreate(&s->clk.b[i]) == cudaSuccess;
+    for (int i = 0; i < 80 && ok; i++) ok = cudaEventCreate(&s->sort_ev[i]) == cudaSuccess;
     s->device_bytes = total;
     if (!ok) {
         fprintf(stderr, "[bz3_b200] bz3_new(%d): device setup failed: %s\n", block_size,
@@ -506,6 +516,8 @@ BZIP3_API void bz3_free(struct bz3_state* s) {
         if (s->clk.a[i]) cudaEventDestroy(s->clk.a[i]);
         if (s->clk.b[i]) cudaEventDestroy(s->clk.b[i]);
     }
+    for (int i = 0; i < 80; i++)
+        if (s->sort_ev[i]) cudaEventDestroy(s->sort_ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -801,6 +813,7 @@ BZIP3_API void bz3_b200_stats_reset(struct bz3_state* s) {
     memset(s->stage_ms, 0, sizeof s->stage_ms);
     s->launches = 0;
     s->sort_records = 0;
+    s->sort_ms = 0;
 }
 BZIP3_API double bz3_b200_stage_ms(struct bz3_state* s, int stage, int decode) {
     if (stage < 0 || stage >= BZ3_STAGE_COUNT) return 0.0;

@@ -441,6 +441,10 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
     __syncthreads();
     if (tid >= 32) {
         // ------------------------------------------------------------------ model thread
+        // Owns one node.  Its order-0 counter and the two order-1 counters it needs next are carried in
+        // registers (only this thread ever writes them), both possible outcomes of the pending update are
+        // computed while the chain warp is busy, so after a byte is published the critical path is:
+        // read byte -> select/commit -> one table load (new order-1 row) -> mix -> two SSE loads -> ptab.
         const int node = tid - 32;                                        // 0 is a dummy
         const int sh = node ? 8 - (31 - __clz(node)) : 8;                 // (256|byte) >> sh == node <=> on the path
         u16* const q0 = cm_smem + node;
@@ -448,38 +452,40 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         u16* const rows = cm_smem + kCmC0 + kCmC1 + (2 * node) * 17;      // + flag * 17 + cell
         int prev1 = 0, prev2 = 0;
         u32 run = 0;
-        int a = 0, b = 0, lo = 0, hi = 0;
         u16* q1 = c1col;
-        u16* cell = rows;
+        u32 a = *q0, b = *q1, d = *q1;
         for (s32 i = 0; i < n; i++) {
-            if (i > 0) {
-                const u32 byte = *vbyte;
-                // (C) learn byte i-1
-                if (node != 0 && ((256u | byte) >> sh) == (u32)node) {
-                    const u32 ones = ((byte >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
-                    *q0 = (u16)cm_adapt_bf((u32)a, ones, 2);
-                    *q1 = (u16)cm_adapt_bf((u32)b, ones, 4);
-                    cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
-                    cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
-                }
-                prev2 = prev1;
-                prev1 = (int)byte;
-            }
             run = (prev1 == prev2) ? run + 1 : 0;
             const int flag = run > 2;
             // (A) predict byte i
-            q1 = c1col + prev1 * 256;
-            a = *q0;
-            b = *q1;
-            const int d = c1col[prev2 * 256];
-            const int p = ((a + b) * 7 + d + d) >> 4;
-            cell = rows + flag * 17 + (p >> 12);
-            lo = cell[0];
-            hi = cell[1];
-            const int sse = lo + (((hi - lo) * (p & 4095)) >> 12);
-            ptab[node] = (u32)(sse * 3 + p) << 14;   // slot 0 is never read
+            const u32 p = ((a + b) * 7 + d + d) >> 4;
+            u16* const cell = rows + flag * 17 + (p >> 12);
+            const u32 lo = cell[0], hi = cell[1];
+            const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
+            ptab[node] = (u32)(sse * 3 + (int)p) << 14;   // slot 0 is never read
             __syncthreads();   // ptab ready
+            // both outcomes of the update, computed while the chain warp walks the byte
+            const u32 a0 = cm_adapt_bf(a, 0u, 2), a1 = cm_adapt_bf(a, 0xFFFFu, 2);
+            const u32 b0 = cm_adapt_bf(b, 0u, 4), b1 = cm_adapt_bf(b, 0xFFFFu, 4);
+            const u32 l0 = cm_adapt_bf(lo, 0u, 6), l1 = cm_adapt_bf(lo, 0xFFFFu, 6);
+            const u32 h0 = cm_adapt_bf(hi, 0u, 6), h1 = cm_adapt_bf(hi, 0xFFFFu, 6);
             __syncthreads();   // byte ready
+            const u32 byte = *vbyte;
+            const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
+            const bool one = ((byte >> (sh - 1)) & 1u) != 0;
+            const u32 na = one ? a1 : a0, nb = one ? b1 : b0;
+            if (on) {   // (C) learn byte i
+                *q0 = (u16)na;
+                *q1 = (u16)nb;
+                cell[0] = (u16)(one ? l1 : l0);
+                cell[1] = (u16)(one ? h1 : h0);
+            }
+            a = on ? na : a;
+            d = on ? nb : b;              // this byte's order-1 counter is the next byte's prev2 counter
+            prev2 = prev1;
+            prev1 = (int)byte;
+            q1 = c1col + prev1 * 256;
+            b = *q1;                      // after the store above in program order (same counter when byte repeats)
         }
         return;
     }

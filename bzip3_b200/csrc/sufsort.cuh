@@ -32,6 +32,9 @@ struct SufsortBuffers {
     u32* temp;    // radix / scan scratch
     u32* d_count; // device scalars (>= 4 u32)
     u32* h_count; // pinned mirror
+    cudaEvent_t* ev = nullptr;  // optional: 2*max_ev events bracketing every radix sort (statistics)
+    int max_ev = 0;
+    int* used_ev = nullptr;
 };
 
 inline size_t sufsort_temp_elems(u32 n) {
@@ -142,7 +145,14 @@ inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const 
     sa_init_keys_kernel<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(T, n, B.key[0]); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     bool in_b = false;
+    int nev = 0;
+    auto mark = [&](int which) {
+        if (B.ev && nev < B.max_ev) cudaEventRecord(B.ev[2 * nev + which], st);
+        if (which == 1 && B.ev && nev < B.max_ev) nev++;
+    };
+    mark(0);
     BZ_CUDA_TRY(rs_sort_pairs<u64>(st, B.key[0], B.val[0], B.key[1], B.val[1], n, 64, B.temp, &in_b, true));
+    mark(1);
     int kc = in_b ? 1 : 0;  // buffer holding the sorted records
     int lc = 0;             // list buffer to write
     RegroupElem ident{0u, 0u};
@@ -167,7 +177,9 @@ inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const 
                                                                   B.key[0]); BZ_NOTE_LAUNCH();
         BZ_CUDA_TRY(cudaGetLastError());
         // sort (key[0], val[vc]) <-> (key[1], val[vc^1])
+        mark(0);
         BZ_CUDA_TRY(rs_sort_pairs<u64>(st, B.key[0], B.val[vc], B.key[1], B.val[vc ^ 1], m, 2 * rank_bits, B.temp, &in_b));
+        mark(1);
         int sk = in_b ? 1 : 0;
         int sv = in_b ? (vc ^ 1) : vc;
         BZ_CUDA_TRY((device_scan<RegroupElem, RegroupOp, RegroupIn, RegroupOut>(
@@ -181,6 +193,7 @@ inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const 
         lc ^= 1;
     }
     if (rounds_out) *rounds_out = rounds;
+    if (B.used_ev) *B.used_ev = nev;
     if (record_passes_out) *record_passes_out = record_passes;
     // primary index = rank of suffix 0 (1-based SA slot)
     BZ_CUDA_TRY(cudaMemcpyAsync(B.h_count, B.isa, sizeof(u32), cudaMemcpyDeviceToHost, st));
