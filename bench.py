@@ -392,7 +392,7 @@ def run_b200_arm(args, rank, world, local_rank):
         cm_enc_ms = stage_total(stage_enc, "cm") / (nb * args.steps)
         avg_n = total / nb
         avg_c = sum(int(e) for e in enc_sizes) / nb
-        dom = "cm_decode_single_kernel" if cm_dec_ms >= cm_enc_ms else "cm_encode_pipelined_kernel"
+        dom = "cm_decode_tree_kernel" if cm_dec_ms >= cm_enc_ms else "cm_encode_chunked_kernel"
         dom_ms = max(cm_dec_ms, cm_enc_ms)
         dom_bytes = avg_n + avg_c  # the coder reads/writes the BWT bytes once and the payload once
         achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0

@@ -825,6 +825,12 @@ BZIP3_API void bz3_b200_last_sort_stats(struct bz3_state* s, uint64_t* records, 
     if (rounds) *rounds = s->sort_rounds;
     if (ms) *ms = s->sort_ms;
 }
+#ifdef BZ_CM_PROFILE
+extern "C" BZIP3_API void bz3_b200_debug_cm_profile(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_cm_prof, sizeof(unsigned long long) * 16);
+}
+#endif
 BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant) {
     if (stage >= 0 && stage < BZ3_STAGE_COUNT) s->variant[stage] = variant;
 }

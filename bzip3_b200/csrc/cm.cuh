@@ -415,6 +415,18 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
     }
 }
 
+#ifdef BZ_CM_PROFILE
+__device__ unsigned long long g_cm_prof[16];
+#define BZ_PROF_DECL unsigned long long _t0 = clock64(), _t1
+#define BZ_PROF(slot) do { _t1 = clock64(); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
+// after a barrier: BAR.SYNC does not block at issue, so make the clock read depend on a post-barrier load
+#define BZ_PROF_AFTER_BAR(slot, ptr) do { unsigned _v = *(ptr); asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"(_t1) : "r"(_v)); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define BZ_PROF_AFTER_BAR(slot, ptr)
+#define BZ_PROF_DECL
+#define BZ_PROF(slot)
+#endif
+
 // ---- tree-parallel decoder ---------------------------------------------------------------------
 // Decoding is one dependent chain: the next context depends on the bit just decoded.  What does not
 // depend on the bits of the current byte is the probability of every one of the 255 tree nodes (no node
@@ -454,6 +466,10 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         u32 run = 0;
         u16* q1 = c1col;
         u32 a = *q0, b = *q1, d = *q1;
+#ifdef BZ_CM_PROFILE
+        unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+        BZ_PROF_DECL;
         for (s32 i = 0; i < n; i++) {
             run = (prev1 == prev2) ? run + 1 : 0;
             const int flag = run > 2;
@@ -463,13 +479,17 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
             const u32 lo = cell[0], hi = cell[1];
             const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
             ptab[node] = (u32)(sse * 3 + (int)p) << 14;   // slot 0 is never read
+            BZ_PROF(0);
             __syncthreads();   // ptab ready
+            BZ_PROF_AFTER_BAR(1, vbyte);
             // both outcomes of the update, computed while the chain warp walks the byte
             const u32 a0 = cm_adapt_bf(a, 0u, 2), a1 = cm_adapt_bf(a, 0xFFFFu, 2);
             const u32 b0 = cm_adapt_bf(b, 0u, 4), b1 = cm_adapt_bf(b, 0xFFFFu, 4);
             const u32 l0 = cm_adapt_bf(lo, 0u, 6), l1 = cm_adapt_bf(lo, 0xFFFFu, 6);
             const u32 h0 = cm_adapt_bf(hi, 0u, 6), h1 = cm_adapt_bf(hi, 0xFFFFu, 6);
+            BZ_PROF(2);
             __syncthreads();   // byte ready
+            BZ_PROF_AFTER_BAR(3, vbyte);
             const u32 byte = *vbyte;
             const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
             const bool one = ((byte >> (sh - 1)) & 1u) != 0;
@@ -487,6 +507,10 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
             q1 = c1col + prev1 * 256;
             b = *q1;                      // after the store above in program order (same counter when byte repeats)
         }
+#ifdef BZ_CM_PROFILE
+        if (tid == 33) for (int k = 0; k < 4; k++) g_cm_prof[k] = _acc[k];          // node 1 (always on the path)
+        if (tid == 32 + 200) for (int k = 0; k < 4; k++) g_cm_prof[4 + k] = _acc[k];   // a depth-7 node
+#endif
         return;
     }
     // ---------------------------------------------------------------------- chain warp (all lanes identical)
@@ -500,8 +524,14 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         code = (code << 8) + add;
     }
     const u32* pt = ptab;
+#ifdef BZ_CM_PROFILE
+    unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    BZ_PROF_DECL;
     for (s32 i = 0; i < n; i++) {
+        BZ_PROF(0);
         __syncthreads();   // ptab ready
+        BZ_PROF_AFTER_BAR(1, vbyte);
         const uint4 g0 = *reinterpret_cast<const uint4*>(pt);
         uint4 gk = *reinterpret_cast<const uint4*>(pt + 4);
         u32 node = 1;
@@ -590,10 +620,10 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
             }
         }
         const u32 byte = node & 255u;
-        if (tid == 0) {
-            *vbyte = byte;
-            out[i] = (u8)byte;
-        }
+        BZ_PROF(2);
+        // every lane holds the same byte: unconditional (convergent) stores of one value to one address
+        *vbyte = byte;
+        out[i] = (u8)byte;
         if (ip - wlo >= 1024) {  // uniform in the warp; the window belongs to this warp alone
             __syncwarp();
             for (int k = tid; k < 1024; k += 32) {
@@ -603,8 +633,13 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
             wlo += 1024;
             __syncwarp();
         }
+        BZ_PROF(3);
         __syncthreads();   // byte ready
+        BZ_PROF_AFTER_BAR(4, vbyte);
     }
+#ifdef BZ_CM_PROFILE
+    if (tid == 0) for (int k = 0; k < 5; k++) g_cm_prof[8 + k] = _acc[k];
+#endif
 }
 
 inline cudaError_t cm_set_smem_attrs() {
