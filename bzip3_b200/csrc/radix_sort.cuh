@@ -182,6 +182,59 @@ rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, 
     }
 }
 
+// Exclusive scan of hist[256][ntiles] in digit-major order in two launches (one CTA per digit row):
+// row totals first, then every row scans itself starting from the sum of the rows before it.
+__global__ void __launch_bounds__(256) rs_row_total_kernel(const u32* __restrict__ hist, u32 ntiles, u32* __restrict__ row_total) {
+    __shared__ u32 red[8];
+    const u32* row = hist + (size_t)blockIdx.x * ntiles;
+    u32 s = 0;
+    for (u32 i = threadIdx.x; i < ntiles; i += 256) s += row[i];
+    s = warp_reduce_sum(s);
+    if (lane_id() == 0) red[warp_id()] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (int k = 0; k < 8; k++) t += red[k];
+        row_total[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) rs_row_scan_kernel(u32* __restrict__ hist, u32 ntiles, const u32* __restrict__ row_total) {
+    __shared__ u32 wsum[8];
+    __shared__ u32 carry_s;
+    const u32 d = blockIdx.x;
+    {   // sum of the totals of rows 0..d-1 (256 values)
+        u32 v = threadIdx.x < d ? row_total[threadIdx.x] : 0u;
+        v = warp_reduce_sum(v);
+        if (lane_id() == 0) wsum[warp_id()] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 t = 0;
+            for (int k = 0; k < 8; k++) t += wsum[k];
+            carry_s = t;
+        }
+        __syncthreads();
+    }
+    u32* row = hist + (size_t)d * ntiles;
+    u32 carry = carry_s;
+    for (u32 base = 0; base < ntiles; base += 256) {
+        const u32 i = base + threadIdx.x;
+        const u32 v = i < ntiles ? row[i] : 0u;
+        const u32 incl = warp_scan_incl(v);
+        __syncthreads();  // wsum reuse
+        if (lane_id() == 31) wsum[warp_id()] = incl;
+        __syncthreads();
+        u32 wp = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u32 t = wsum[k];
+            if ((u32)k < warp_id()) wp += t;
+            tot += t;
+        }
+        if (i < ntiles) row[i] = carry + wp + incl - v;
+        carry += tot;
+    }
+}
+
 template <typename K>
 inline u32 rs_num_tiles(u32 n) {
     constexpr u32 TILE = kRsThreads * RsCfg<K>::kItems;
@@ -196,7 +249,7 @@ inline size_t rs_scatter_smem() {
 template <typename K>
 inline size_t rs_temp_elems(u32 n) {
     size_t h = (size_t)256 * rs_num_tiles<K>(n);
-    return h + scan_temp_elems((u32)h) + 16;
+    return h + 256 /* row totals */ + scan_temp_elems((u32)h) + 16;
 }
 
 // One stable pass on digit bits [shift, shift+bits).
@@ -210,8 +263,9 @@ cudaError_t rs_pass(cudaStream_t st, const K* kin, ValGen vgen, K* kout, u32* vo
     rs_tile_hist_kernel<K><<<ntiles, kRsThreads, 0, st>>>(kin, n, shift, mask, hist, ntiles); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     const u32 hn = 256 * ntiles;
-    BZ_CUDA_TRY((device_scan<u32, SumU32, PtrIn<u32>, PtrOutExcl<u32>>(st, PtrIn<u32>{hist}, PtrOutExcl<u32>{hist}, hn,
-                                                                      0u, SumU32{}, hist + hn)));
+    rs_row_total_kernel<<<256, 256, 0, st>>>(hist, ntiles, hist + hn); BZ_NOTE_LAUNCH();
+    rs_row_scan_kernel<<<256, 256, 0, st>>>(hist, ntiles, hist + hn); BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
     auto kern = rs_scatter_kernel<K, KOUT, VOUT, ValGen>;
     const size_t smem = rs_scatter_smem<K>();
     // set every time: the attribute is per device and a process may drive several GPUs
