@@ -276,6 +276,8 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
 cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s32 n) {
     if (s->variant[BZ3_STAGE_CM] == 1)
         cm_decode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+    else if (s->variant[BZ3_STAGE_CM] == 3)
+        cm_decode_paths_kernel<<<1, kCmDecPathsThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else
         cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     BZ_NOTE_LAUNCH();

@@ -642,12 +642,191 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
 #endif
 }
 
+// ---- all-paths decoder ---------------------------------------------------------------------------
+// Same model phase as above, but no chain warp: after the 255 node probabilities of a byte are known,
+// thread v (0..255) walks the root-to-leaf path of byte value v with its own, compile-time-known-per-
+// thread bits: 8 x (mul.hi, compare, update, predicated renormalisation shift).  A path is "alive"
+// while every decision the coder would take on it (code <= split) equals the path's bit; exactly one
+// path stays alive to the leaf -- that thread publishes the byte and the new coder state.  Nothing on
+// the walk is selected by a decoded bit, so the serial select chain of the chain-warp kernel disappears
+// and the walk costs ~8 x 35 cycles.  Warps whose 32 leaves are all dead leave early (a warp shares the
+// top three bits).  Two situations fall back to the exact serial byte decoder on thread 0: a step that
+// needs a second shift, and the last 8 bytes of the stream (the reference adds -1 past the end).
+constexpr int kCmDecPathsThreads = 256;
+
+__global__ void __launch_bounds__(kCmDecPathsThreads) cm_decode_paths_kernel(const u8* __restrict__ in, s32 insize,
+                                                                            u8* __restrict__ out, s32 n) {
+    extern __shared__ __align__(16) u16 cm_smem[];
+    u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [256]  P << 14 per node
+    u8* scode = reinterpret_cast<u8*>(ptab + 256);              // [2048] window of the compressed stream
+    volatile u32* st = reinterpret_cast<volatile u32*>(scode + 2048);  // 2 slots of 8: [0]=byte [1]=low [2]=range [3]=code [4]=ip
+    cm_tables_init_smem(cm_smem);
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 2048; k += kCmDecPathsThreads) scode[k] = (k < insize) ? in[k] : 0;
+    __syncthreads();
+    if (tid == 0) {
+        s32 ip = 0;
+        u32 code = 0;
+        for (int k = 0; k < 4; k++) {
+            const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;  // read_in() past the end adds -1
+            ip += (ip < insize);
+            code = (code << 8) + add;
+        }
+        st[1] = 0u;
+        st[2] = 0xFFFFFFFFu;
+        st[3] = code;
+        st[4] = (u32)ip;
+    }
+    // model role: owner of node `tid` (0 is a dummy)
+    const int node = tid;
+    const int sh = node ? 8 - (31 - __clz(node)) : 8;
+    u16* const q0 = cm_smem + node;
+    u16* const c1col = cm_smem + kCmC0 + node;
+    u16* const rows = cm_smem + kCmC0 + kCmC1 + (2 * node) * 17;
+    int prev1 = 0, prev2 = 0;
+    u32 run = 0;
+    u16* q1 = c1col;
+    u32 a = *q0, b = *q1, d = *q1;
+    // path role: leaf value v = tid; node visited at level k is (256 | v) >> (8 - k)
+    const u32 v = (u32)tid;
+    const u32* const scode32 = reinterpret_cast<const u32*>(scode);
+    s32 wlo = 0;
+    for (s32 i = 0; i < n; i++) {
+        run = (prev1 == prev2) ? run + 1 : 0;
+        const int flag = run > 2;
+        // (A) predict byte i
+        const u32 p = ((a + b) * 7 + d + d) >> 4;
+        u16* const cell = rows + flag * 17 + (p >> 12);
+        const u32 lo = cell[0], hi = cell[1];
+        const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
+        ptab[node] = (u32)(sse * 3 + (int)p) << 14;
+        __syncthreads();   // S1: ptab and coder state ready
+        // ---- walk (coder state is double buffered: read slot i&1, write slot (i+1)&1)
+        volatile u32* const sr = st + 8 * (i & 1);
+        volatile u32* const sw = st + 8 * ((i + 1) & 1);
+        u32 low = sr[1], range = sr[2], code = sr[3];
+        const s32 ip = (s32)sr[4];
+        const bool tail = ip + 8 > insize;             // uniform
+        u32 P0 = ptab[1], P1 = ptab[(256u | v) >> 7], P2 = ptab[(256u | v) >> 6], P3 = ptab[(256u | v) >> 5];
+        u32 P4 = ptab[(256u | v) >> 4], P5 = ptab[(256u | v) >> 3], P6 = ptab[(256u | v) >> 2], P7 = ptab[(256u | v) >> 1];
+        // next 8 stream bytes, big-endian in (chi, clo)
+        u32 chi, clo;
+        {
+            const u32 w = ((u32)ip >> 2) & 511u, sft = ((u32)ip & 3u) * 8u;
+            const u32 a0 = scode32[w], a1 = scode32[(w + 1) & 511u], a2 = scode32[(w + 2) & 511u];
+            chi = __byte_perm(__funnelshift_r(a0, a1, sft), 0u, 0x0123);
+            clo = __byte_perm(__funnelshift_r(a1, a2, sft), 0u, 0x0123);
+        }
+        bool ok = true, dbl = false;
+        u32 nsh = 0;
+#define BZ_PATH_STEP(K, PK)                                                            \
+        {                                                                              \
+            const bool bk = ((v >> (7 - (K))) & 1u) != 0;                              \
+            const u32 x = __umulhi(range, (PK));                                       \
+            const u32 mid = low + x;                                                   \
+            ok = ok && ((code <= mid) == bk);                                          \
+            if (bk) {                                                                  \
+                range = x;                                                             \
+            } else {                                                                   \
+                low = mid + 1u;                                                        \
+                range = range - x - 1u;                                                \
+            }                                                                          \
+            const bool s_ = ((low ^ (low + range)) < (1u << 24));                      \
+            if (s_) {                                                                  \
+                low <<= 8;                                                             \
+                range = (range << 8) | 0xFFu;                                          \
+                code = __funnelshift_l(chi, code, 8);                                  \
+                chi = __funnelshift_l(clo, chi, 8);                                    \
+                clo <<= 8;                                                             \
+                nsh++;                                                                 \
+            }                                                                          \
+            dbl = dbl || (ok && s_ && ((low ^ (low + range)) < (1u << 24)));           \
+        }
+        BZ_PATH_STEP(0, P0)
+        BZ_PATH_STEP(1, P1)
+        BZ_PATH_STEP(2, P2)
+        if (__any_sync(kFullMask, ok)) {          // a warp shares the top three bits: 7 of 8 warps stop here
+            BZ_PATH_STEP(3, P3)
+            BZ_PATH_STEP(4, P4)
+            BZ_PATH_STEP(5, P5)
+            BZ_PATH_STEP(6, P6)
+            BZ_PATH_STEP(7, P7)
+        } else {
+            ok = false;
+        }
+#undef BZ_PATH_STEP
+        if (ok && !dbl && !tail) {
+            sw[0] = v;
+            sw[1] = low;
+            sw[2] = range;
+            sw[3] = code;
+            sw[4] = (u32)ip + nsh;
+        }
+        const int fallback = __syncthreads_or((dbl || tail) ? 1 : 0);   // S2: byte and state ready (or nobody won)
+        if (fallback) {
+            if (tid == 0) {   // exact serial decoder for this byte (reference loop)
+                u32 flow = sr[1], fhigh = sr[1] + sr[2], fcode = sr[3];
+                s32 fip = (s32)sr[4];
+                u32 nd = 1;
+                for (int k = 0; k < 8; k++) {
+                    const u32 mid = flow + __umulhi(fhigh - flow, ptab[nd]);
+                    const bool bit = fcode <= mid;
+                    if (bit) fhigh = mid; else flow = mid + 1u;
+                    nd = nd * 2 + (bit ? 1u : 0u);
+                    while ((flow ^ fhigh) < (1u << 24)) {
+                        flow <<= 8;
+                        fhigh = (fhigh << 8) | 0xFFu;
+                        const u32 add = (fip < insize) ? (u32)scode[fip & 2047] : 0xFFFFFFFFu;
+                        fip += (fip < insize);
+                        fcode = (fcode << 8) + add;
+                    }
+                }
+                sw[0] = nd & 255u;
+                sw[1] = flow;
+                sw[2] = fhigh - flow;
+                sw[3] = fcode;
+                sw[4] = (u32)fip;
+            }
+            __syncthreads();
+        }
+        const u32 byte = sw[0];
+        if (tid == 0) out[i] = (u8)byte;
+        // both outcomes of the update were not precomputed here (no idle phase): learn directly
+        const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
+        const u32 ones = ((byte >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
+        const u32 na = cm_adapt_bf(a, ones, 2), nb = cm_adapt_bf(b, ones, 4);
+        if (on) {   // (C) learn byte i
+            *q0 = (u16)na;
+            *q1 = (u16)nb;
+            cell[0] = (u16)cm_adapt_bf(lo, ones, 6);
+            cell[1] = (u16)cm_adapt_bf(hi, ones, 6);
+        }
+        a = on ? na : a;
+        d = on ? nb : b;
+        prev2 = prev1;
+        prev1 = (int)byte;
+        q1 = c1col + prev1 * 256;
+        b = *q1;
+        // keep the stream window ahead of the read position (uniform)
+        const s32 nip = (s32)sw[4];
+        if (nip - wlo >= 1024) {
+            __syncthreads();
+            for (int k = tid; k < 1024; k += kCmDecPathsThreads) {
+                const s32 src = wlo + 2048 + k;
+                scode[src & 2047] = (src < insize) ? in[src] : 0;
+            }
+            wlo += 1024;
+        }
+    }
+}
+
 inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     return cudaSuccess;
 }
 
