@@ -178,6 +178,18 @@ BZ_D u32 cm_adapt_bf(u32 v, u32 ones /* bit ? 0xFFFF : 0 */, int rate) {
     return ones ? v + u : v - u;
 }
 
+#ifdef BZ_CM_PROFILE
+__device__ unsigned long long g_cm_prof[16];
+#define BZ_PROF_DECL unsigned long long _t0 = clock64(), _t1
+#define BZ_PROF(slot) do { _t1 = clock64(); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
+// after a barrier: BAR.SYNC does not block at issue, so make the clock read depend on a post-barrier load
+#define BZ_PROF_AFTER_BAR(slot, ptr) do { unsigned _v = *(ptr); asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"(_t1) : "r"(_v)); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define BZ_PROF_AFTER_BAR(slot, ptr)
+#define BZ_PROF_DECL
+#define BZ_PROF(slot)
+#endif
+
 // ---- chunked pipelined encoder -----------------------------------------------------------------
 // Warp 0 runs the model: lane d (0..7) owns tree depth d, i.e. bit position d of every byte.  A node
 // of depth d is only ever coded at bit position d, so the eight lanes touch disjoint counters and
@@ -303,7 +315,13 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
     u32 run = 0;
     u32 low = 0, range = 0xFFFFFFFFu;
     s32 op = 0;
+#ifdef BZ_CM_PROFILE
+    unsigned long long _busy = 0;
+#endif
     for (s32 it = 0; it < nchunks + 2; it++) {
+#ifdef BZ_CM_PROFILE
+        const unsigned long long _tb = clock64();
+#endif
         if (warp == 0) {
             if (it < nchunks) {
                 const s32 base = it * kCmEncChunk;
@@ -404,8 +422,14 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                 }
             }
         }
+#ifdef BZ_CM_PROFILE
+        _busy += clock64() - _tb;
+#endif
         __syncthreads();
     }
+#ifdef BZ_CM_PROFILE
+    if (lane == 0) g_cm_prof[13 + (warp == 0 ? 0 : warp == 2 ? 1 : 2)] = _busy;   // stage1, stage2, coder
+#endif
     if (threadIdx.x == 32) {
         for (int k = 0; k < 4; k++) {  // flush (reference src/libbz3.c:425-432)
             out[op++] = (u8)(low >> 24);
@@ -414,18 +438,6 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
         *out_size = op;
     }
 }
-
-#ifdef BZ_CM_PROFILE
-__device__ unsigned long long g_cm_prof[16];
-#define BZ_PROF_DECL unsigned long long _t0 = clock64(), _t1
-#define BZ_PROF(slot) do { _t1 = clock64(); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
-// after a barrier: BAR.SYNC does not block at issue, so make the clock read depend on a post-barrier load
-#define BZ_PROF_AFTER_BAR(slot, ptr) do { unsigned _v = *(ptr); asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"(_t1) : "r"(_v)); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
-#else
-#define BZ_PROF_AFTER_BAR(slot, ptr)
-#define BZ_PROF_DECL
-#define BZ_PROF(slot)
-#endif
 
 // ---- tree-parallel decoder ---------------------------------------------------------------------
 // Decoding is one dependent chain: the next context depends on the bit just decoded.  What does not
@@ -720,26 +732,22 @@ __global__ void __launch_bounds__(kCmDecPathsThreads) cm_decode_paths_kernel(con
         bool ok = true, dbl = false;
         u32 nsh = 0;
 #define BZ_PATH_STEP(K, PK)                                                            \
-        {                                                                              \
+        {   /* branch-free: lanes of a warp take different bits and shift at different steps */ \
             const bool bk = ((v >> (7 - (K))) & 1u) != 0;                              \
             const u32 x = __umulhi(range, (PK));                                       \
             const u32 mid = low + x;                                                   \
             ok = ok && ((code <= mid) == bk);                                          \
-            if (bk) {                                                                  \
-                range = x;                                                             \
-            } else {                                                                   \
-                low = mid + 1u;                                                        \
-                range = range - x - 1u;                                                \
-            }                                                                          \
+            low = bk ? low : mid + 1u;                                                 \
+            range = bk ? x : range - x - 1u;                                           \
             const bool s_ = ((low ^ (low + range)) < (1u << 24));                      \
-            if (s_) {                                                                  \
-                low <<= 8;                                                             \
-                range = (range << 8) | 0xFFu;                                          \
-                code = __funnelshift_l(chi, code, 8);                                  \
-                chi = __funnelshift_l(clo, chi, 8);                                    \
-                clo <<= 8;                                                             \
-                nsh++;                                                                 \
-            }                                                                          \
+            const u32 ncode = __funnelshift_l(chi, code, 8);                           \
+            const u32 nchi = __funnelshift_l(clo, chi, 8);                             \
+            low = s_ ? (low << 8) : low;                                               \
+            range = s_ ? ((range << 8) | 0xFFu) : range;                               \
+            code = s_ ? ncode : code;                                                  \
+            chi = s_ ? nchi : chi;                                                     \
+            clo = s_ ? (clo << 8) : clo;                                               \
+            nsh += s_ ? 1u : 0u;                                                       \
             dbl = dbl || (ok && s_ && ((low ^ (low + range)) < (1u << 24)));           \
         }
         BZ_PATH_STEP(0, P0)

@@ -17,4 +17,5 @@ with bzip3_b200.Bz3State(n) as s:
     p = [x / n for x in prof]
     print("cycles/byte  model(node1): A=%.0f wait_ptab=%.0f precompute=%.0f wait_byte=%.0f" % tuple(p[0:4]))
     print("cycles/byte  model(node200): A=%.0f wait_ptab=%.0f precompute=%.0f wait_byte=%.0f" % tuple(p[4:8]))
+    print("cycles/byte  encoder busy: stage1=%.0f stage2=%.0f coder=%.0f" % tuple(p[13:16]))
     print("cycles/byte  chain: loop=%.0f wait_ptab=%.0f B=%.0f publish+refill=%.0f wait_byte=%.0f" % tuple(p[8:13]))
