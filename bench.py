@@ -219,7 +219,7 @@ def run_reference_arm(args, rank, world):
                                    f"{min(jobs, len(blocks))} pthreads (host has {host_threads()} usable cores)"},
         "e2e": {"value": round(val, 3), "unit": "MiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 # ------------------------------------------------------------------------------------------- B200 arm
@@ -445,7 +445,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        _emit(out)
     for s in states:
         s.close()
     if dist:
@@ -453,7 +453,29 @@ def run_b200_arm(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the duration of the run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = json.dumps(obj)
+    if _REAL_STDOUT is not None:
+        _REAL_STDOUT.write(line + "\n")
+        _REAL_STDOUT.flush()
+    else:
+        print(line, flush=True)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
