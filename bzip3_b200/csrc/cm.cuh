@@ -228,13 +228,15 @@ BZ_D void rc_fast_step(u32& low, u32& range, u32& x, u32& tmin, u32 bit, u32 mne
     asm volatile(
         "{\n\t"
         ".reg .pred pb;\n\t"
-        ".reg .u32 nx, hi, t;\n\t"
+        ".reg .u32 hi, t, r0;\n\t"
         "setp.ne.u32 pb, %4, 0;\n\t"
-        "not.b32 nx, %2;\n\t"
-        "@pb mov.u32 %1, %2;\n\t"          // bit 1: range = x
-        "@!pb add.u32 %1, %1, nx;\n\t"     // bit 0: range -= x + 1
-        "mul.hi.u32 %2, %1, %5;\n\t"       // product for the next decision
-        "@!pb sub.u32 %0, %0, nx;\n\t"     // bit 0: low += x + 1
+        "sub.u32 r0, %1, %2;\n\t"          // range - x - 1 (one 3-input add)
+        "add.u32 r0, r0, -1;\n\t"
+        "selp.u32 %1, %2, r0, pb;\n\t"     // bit 1: range = x    bit 0: range -= x + 1
+        "mul.hi.u32 r0, %1, %5;\n\t"       // product for the next decision
+        "@!pb add.u32 %0, %0, %2;\n\t"     // bit 0: low += x + 1
+        "@!pb add.u32 %0, %0, 1;\n\t"
+        "mov.u32 %2, r0;\n\t"
         "add.u32 hi, %0, %1;\n\t"
         "xor.b32 t, %0, hi;\n\t"
         "min.u32 %3, %3, t;\n\t"
@@ -386,9 +388,13 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                     const uint4 ca = a, cb = b;
                     const u32 cs = sym;
                     const s32 kn = (k + 1 < len) ? k + 1 : k;  // the last byte re-reads itself; that product is unused
-                    a = pv[2 * kn];
-                    b = pv[2 * kn + 1];
-                    sym = sb[kn];
+                    {   // pinned prefetch of the next byte's entries: issued before this byte's decisions, not after
+                        const u32 ap = (u32)__cvta_generic_to_shared(pv + 2 * kn);
+                        const u32 sp = (u32)__cvta_generic_to_shared(sb + kn);
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(ap));
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(ap));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym) : "r"(sp));
+                    }
                     if (MODE == 0) {
                         const u32 low0 = low, range0 = range, x0 = x;
                         u32 tmin = 0xFFFFFFFFu;
