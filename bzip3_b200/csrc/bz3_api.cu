@@ -145,11 +145,6 @@ struct LaunchScope {  // folds this thread's launch count into the state
 inline void put32(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); }
 inline u32 get32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
 
-#define BZ_TRY_ERR(expr)                                 \
-    do {                                                 \
-        if ((expr) != cudaSuccess) return cudaErrorUnknown; \
-    } while (0)
-
 // ---------------------------------------------------------------------------------- stage drivers
 cudaError_t run_crc(bz3_state* s, const u8* d_in, u32 n, u32* crc_out) {
     BZ_CUDA_TRY(crc_launch(s->stream, d_in, n, 1u, s->d_scal + 32));
