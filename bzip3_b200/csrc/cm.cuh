@@ -456,13 +456,13 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
 // Two __syncthreads per byte (ptab ready / byte ready).  The compressed bytes are staged through a
 // 2 KiB shared window owned by warp 0, so the renormalisation never waits on global memory.
 constexpr int kCmDecThreads = 288;
-constexpr size_t kCmDecSmemBytes = (size_t)kCmTableU16 * 2 + 256 * 4 + 2048 + 64;
+constexpr size_t kCmDecSmemBytes = (size_t)kCmTableU16 * 2 + 2 * 256 * 4 + 2048 + 64;
 
 __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8* __restrict__ in, s32 insize,
                                                                       u8* __restrict__ out, s32 n) {
     extern __shared__ __align__(16) u16 cm_smem[];
-    u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [256]  P << 14 per node
-    u8* scode = reinterpret_cast<u8*>(ptab + 256);              // [2048] window of the compressed stream
+    u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [2][256]  P << 14 per node; byte i uses half i&1
+    u8* scode = reinterpret_cast<u8*>(ptab + 512);              // [2048] window of the compressed stream
     volatile u32* vbyte = reinterpret_cast<volatile u32*>(scode + 2048);  // last decoded byte
     cm_tables_init_smem(cm_smem);
     const int tid = threadIdx.x;
@@ -471,10 +471,11 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
     __syncthreads();
     if (tid >= 32) {
         // ------------------------------------------------------------------ model thread
-        // Owns one node.  Its order-0 counter and the two order-1 counters it needs next are carried in
-        // registers (only this thread ever writes them), both possible outcomes of the pending update are
-        // computed while the chain warp is busy, so after a byte is published the critical path is:
-        // read byte -> select/commit -> one table load (new order-1 row) -> mix -> two SSE loads -> ptab.
+        // Owns one node; its counters are carried in registers (only this thread writes them).  While the
+        // chain warp walks byte i the thread (1) computes both outcomes of its pending update and
+        // (2) SPECULATES that byte i repeats byte i-1 -- the common case in BWT output -- and predicts
+        // byte i+1 under that hypothesis into the other half of ptab.  On a hit the chain continues at
+        // once (no predict phase, no second barrier); on a miss the speculation is simply overwritten.
         const int node = tid - 32;                                        // 0 is a dummy
         const int sh = node ? 8 - (31 - __clz(node)) : 8;                 // (256|byte) >> sh == node <=> on the path
         u16* const q0 = cm_smem + node;
@@ -484,30 +485,50 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         u32 run = 0;
         u16* q1 = c1col;
         u32 a = *q0, b = *q1, d = *q1;
-#ifdef BZ_CM_PROFILE
-        unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-        BZ_PROF_DECL;
+        u32 lo = 0, hi = 0;
+        u16* cell = rows;
+        bool have = false;   // ptab of the current byte was already produced by the speculation
         for (s32 i = 0; i < n; i++) {
-            run = (prev1 == prev2) ? run + 1 : 0;
-            const int flag = run > 2;
-            // (A) predict byte i
-            const u32 p = ((a + b) * 7 + d + d) >> 4;
-            u16* const cell = rows + flag * 17 + (p >> 12);
-            const u32 lo = cell[0], hi = cell[1];
-            const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
-            ptab[node] = (u32)(sse * 3 + (int)p) << 14;   // slot 0 is never read
-            BZ_PROF(0);
-            __syncthreads();   // ptab ready
-            BZ_PROF_AFTER_BAR(1, vbyte);
-            // both outcomes of the update, computed while the chain warp walks the byte
+            if (!have) {
+                run = (prev1 == prev2) ? run + 1 : 0;
+                const int flag = run > 2;
+                // (A) predict byte i
+                const u32 p = ((a + b) * 7 + d + d) >> 4;
+                cell = rows + flag * 17 + (p >> 12);
+                lo = cell[0];
+                hi = cell[1];
+                const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
+                ptab[(i & 1) * 256 + node] = (u32)(sse * 3 + (int)p) << 14;   // slot 0 is never read
+                __syncthreads();   // ptab ready
+            }
+            // both outcomes of the update of byte i
             const u32 a0 = cm_adapt_bf(a, 0u, 2), a1 = cm_adapt_bf(a, 0xFFFFu, 2);
             const u32 b0 = cm_adapt_bf(b, 0u, 4), b1 = cm_adapt_bf(b, 0xFFFFu, 4);
             const u32 l0 = cm_adapt_bf(lo, 0u, 6), l1 = cm_adapt_bf(lo, 0xFFFFu, 6);
             const u32 h0 = cm_adapt_bf(hi, 0u, 6), h1 = cm_adapt_bf(hi, 0xFFFFu, 6);
-            BZ_PROF(2);
+            // speculation: byte i == prev1.  Then prev1' = prev2' = prev1, both order-1 inputs of byte i+1 are
+            // this thread's current order-1 counter (updated if the node is on the path of prev1).
+            const u32 hyp = (u32)prev1;
+            const bool on_h = node != 0 && ((256u | hyp) >> sh) == (u32)node;
+            const bool one_h = ((hyp >> (sh - 1)) & 1u) != 0;
+            const u32 a_s = on_h ? (one_h ? a1 : a0) : a;
+            const u32 b_s = on_h ? (one_h ? b1 : b0) : b;
+            const u32 run_s = run + 1u;   // run rule (src/libbz3.c:367-370) applied to (prev1, prev1)
+            const int flag_s = run_s > 2;
+            const u32 p_s = ((a_s + b_s) * 7 + b_s + b_s) >> 4;
+            u16* const cell_s = rows + flag_s * 17 + (p_s >> 12);
+            u32 lo_s = cell_s[0], hi_s = cell_s[1];
+            {
+                const u32 nl = one_h ? l1 : l0, nh = one_h ? h1 : h0;   // what byte i would leave in cell[0], cell[1]
+                const bool same = on_h && cell_s == cell, up = on_h && cell_s == cell + 1, dn = on_h && cell_s + 1 == cell;
+                lo_s = same ? nl : (up ? nh : lo_s);
+                hi_s = same ? nh : (dn ? nl : hi_s);
+            }
+            {
+                const int sse = (int)lo_s + ((((int)hi_s - (int)lo_s) * (int)(p_s & 4095)) >> 12);
+                ptab[((i + 1) & 1) * 256 + node] = (u32)(sse * 3 + (int)p_s) << 14;
+            }
             __syncthreads();   // byte ready
-            BZ_PROF_AFTER_BAR(3, vbyte);
             const u32 byte = *vbyte;
             const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
             const bool one = ((byte >> (sh - 1)) & 1u) != 0;
@@ -518,17 +539,25 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
                 cell[0] = (u16)(one ? l1 : l0);
                 cell[1] = (u16)(one ? h1 : h0);
             }
-            a = on ? na : a;
-            d = on ? nb : b;              // this byte's order-1 counter is the next byte's prev2 counter
-            prev2 = prev1;
-            prev1 = (int)byte;
-            q1 = c1col + prev1 * 256;
-            b = *q1;                      // after the store above in program order (same counter when byte repeats)
+            have = byte == hyp;   // uniform across the CTA
+            if (have) {
+                a = a_s;
+                b = b_s;
+                d = b_s;
+                lo = lo_s;
+                hi = hi_s;
+                cell = cell_s;
+                run = run_s;
+                prev2 = prev1;   // == byte
+            } else {
+                a = on ? na : a;
+                d = on ? nb : b;              // this byte's order-1 counter is the next byte's prev2 counter
+                prev2 = prev1;
+                prev1 = (int)byte;
+                q1 = c1col + prev1 * 256;
+                b = *q1;                      // after the store above in program order
+            }
         }
-#ifdef BZ_CM_PROFILE
-        if (tid == 33) for (int k = 0; k < 4; k++) g_cm_prof[k] = _acc[k];          // node 1 (always on the path)
-        if (tid == 32 + 200) for (int k = 0; k < 4; k++) g_cm_prof[4 + k] = _acc[k];   // a depth-7 node
-#endif
         return;
     }
     // ---------------------------------------------------------------------- chain warp (all lanes identical)
@@ -541,15 +570,11 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         ip += (ip < insize);
         code = (code << 8) + add;
     }
-    const u32* pt = ptab;
-#ifdef BZ_CM_PROFILE
-    unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-    BZ_PROF_DECL;
+    bool have = false;
+    u32 prevb = 0;
     for (s32 i = 0; i < n; i++) {
-        BZ_PROF(0);
-        __syncthreads();   // ptab ready
-        BZ_PROF_AFTER_BAR(1, vbyte);
+        if (!have) __syncthreads();   // ptab ready (skipped when the speculation of the model threads hit)
+        const u32* pt = ptab + (i & 1) * 256;
         const uint4 g0 = *reinterpret_cast<const uint4*>(pt);
         uint4 gk = *reinterpret_cast<const uint4*>(pt + 4);
         u32 node = 1;
@@ -638,7 +663,6 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
             }
         }
         const u32 byte = node & 255u;
-        BZ_PROF(2);
         // every lane holds the same byte: unconditional (convergent) stores of one value to one address
         *vbyte = byte;
         out[i] = (u8)byte;
@@ -651,13 +675,10 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
             wlo += 1024;
             __syncwarp();
         }
-        BZ_PROF(3);
         __syncthreads();   // byte ready
-        BZ_PROF_AFTER_BAR(4, vbyte);
+        have = byte == prevb;
+        prevb = byte;
     }
-#ifdef BZ_CM_PROFILE
-    if (tid == 0) for (int k = 0; k < 5; k++) g_cm_prof[8 + k] = _acc[k];
-#endif
 }
 
 // ---- all-paths decoder ---------------------------------------------------------------------------
