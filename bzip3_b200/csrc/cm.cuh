@@ -149,7 +149,7 @@ BZ_HD void cm_decode_serial(const CmTables& t, const u8* in, s32 insize, u8* out
     }
 }
 
-#if defined(__CUDACC__)
+#if defined(BZ_DEVICE_CODE)
 
 constexpr int kCmThreads = 64;
 constexpr size_t kCmSmemBytes = (size_t)kCmTableU16 * 2 + 64;
@@ -160,13 +160,13 @@ BZ_D void cm_tables_init_smem(u16* tab) {
 
 // ---- single-lane kernels: the literal chain, tables in shared memory (used as on-device cross-check)
 __global__ void __launch_bounds__(kCmThreads) cm_encode_single_kernel(const u8* in, s32 n, u8* out, s32* out_size) {
-    extern __shared__ __align__(16) u16 cm_smem[];
+    BZ_DYN_SMEM(u16, cm_smem);
     cm_tables_init_smem(cm_smem);
     __syncthreads();
     if (threadIdx.x == 0) *out_size = cm_encode_serial(cm_tables_at(cm_smem), in, n, out);
 }
 __global__ void __launch_bounds__(kCmThreads) cm_decode_single_kernel(const u8* in, s32 insize, u8* out, s32 n) {
-    extern __shared__ __align__(16) u16 cm_smem[];
+    BZ_DYN_SMEM(u16, cm_smem);
     cm_tables_init_smem(cm_smem);
     __syncthreads();
     if (threadIdx.x == 0) cm_decode_serial(cm_tables_at(cm_smem), in, insize, out, n);
@@ -209,9 +209,13 @@ constexpr size_t kCmEncSmemBytes = (size_t)kCmTableU16 * 2 + 2 * (size_t)kCmEncC
 // NEXT decision before the (rare) renormalisation test of the current one has resolved, which takes the
 // test off the critical recurrence  range -> mul.hi -> range.
 BZ_D u32 mulhi_pinned(u32 a, u32 b) {
+#if defined(BZ_EMU)
+    return __umulhi(a, b);
+#else
     u32 r;
     asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
+#endif
 }
 
 // ---- range coder lane -------------------------------------------------------------------------
@@ -225,6 +229,12 @@ BZ_D u32 mulhi_pinned(u32 a, u32 b) {
 // Recurrence in (low, range) form:  x = umulhi(range, P << 14)  ( == (range * P) >> 18 ),
 //     bit 1: range = x            bit 0: low += x + 1, range -= x + 1
 BZ_D void rc_fast_step(u32& low, u32& range, u32& x, u32& tmin, u32 bit, u32 mnext) {
+#if defined(BZ_EMU)
+    if (bit) range = x; else { low += x + 1u; range -= x + 1u; }
+    x = __umulhi(range, mnext);
+    const u32 t = low ^ (low + range);
+    tmin = t < tmin ? t : tmin;
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred pb;\n\t"
@@ -243,12 +253,18 @@ BZ_D void rc_fast_step(u32& low, u32& range, u32& x, u32& tmin, u32 bit, u32 mne
         "}"
         : "+r"(low), "+r"(range), "+r"(x), "+r"(tmin)
         : "r"(bit), "r"(mnext));
+#endif
 }
 
 // exact tier, one decision: same recurrence, then the renormalisation of the reference.  range < 2^24 is
 // necessary for the top bytes of low and low+range to agree, so that cheap test guards the loop.
 BZ_D void rc_exact_step(u32& low, u32& range, u32& x, s32& op, u32 bit, u32 mnext, u8* __restrict__ out) {
     u32 slow;
+#if defined(BZ_EMU)
+    if (bit) range = x; else { low += x + 1u; range -= x + 1u; }
+    x = __umulhi(range, mnext);
+    slow = range < 0x1000000u;
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred pb, ps;\n\t"
@@ -264,6 +280,7 @@ BZ_D void rc_exact_step(u32& low, u32& range, u32& x, s32& op, u32 bit, u32 mnex
         "}"
         : "+r"(low), "+r"(range), "+r"(x), "=r"(slow)
         : "r"(bit), "r"(mnext));
+#endif
     if (slow) {
         u32 high = low + range;
         while ((low ^ high) < (1u << 24)) {
@@ -300,7 +317,7 @@ __device__ __noinline__ uint4 rc_exact_byte(u32 low, u32 range, s32 op, u32 sym,
 template <int MODE>
 __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const u8* __restrict__ in, s32 n,
                                                                          u8* __restrict__ out, s32* out_size) {
-    extern __shared__ __align__(16) u16 cm_smem[];
+    BZ_DYN_SMEM(u16, cm_smem);
     u32* pbuf = reinterpret_cast<u32*>(cm_smem + kCmTableU16);                 // [2][chunk * 8]  P << 14
     u16* pmid = reinterpret_cast<u16*>(pbuf + 2 * kCmEncChunk * 8);            // [2][chunk * 8]  p
     u8* sbytes = reinterpret_cast<u8*>(pmid + 2 * kCmEncChunk * 8);            // [3][chunk]
@@ -389,11 +406,17 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                     const u32 cs = sym;
                     const s32 kn = (k + 1 < len) ? k + 1 : k;  // the last byte re-reads itself; that product is unused
                     {   // pinned prefetch of the next byte's entries: issued before this byte's decisions, not after
+#if defined(BZ_EMU)
+                        a = pv[2 * kn];
+                        b = pv[2 * kn + 1];
+                        sym = sb[kn];
+#else
                         const u32 ap = (u32)__cvta_generic_to_shared(pv + 2 * kn);
                         const u32 sp = (u32)__cvta_generic_to_shared(sb + kn);
                         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(ap));
                         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(ap));
                         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym) : "r"(sp));
+#endif
                     }
                     if (MODE == 0) {
                         const u32 low0 = low, range0 = range, x0 = x;
@@ -460,10 +483,12 @@ constexpr size_t kCmDecSmemBytes = (size_t)kCmTableU16 * 2 + 2 * 256 * 4 + 2048 
 
 __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8* __restrict__ in, s32 insize,
                                                                       u8* __restrict__ out, s32 n) {
-    extern __shared__ __align__(16) u16 cm_smem[];
+    BZ_DYN_SMEM(u16, cm_smem);
     u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [2][256]  P << 14 per node; byte i uses half i&1
     u8* scode = reinterpret_cast<u8*>(ptab + 512);              // [2048] window of the compressed stream
-    volatile u32* vbyte = reinterpret_cast<volatile u32*>(scode + 2048);  // last decoded byte
+    // decoded byte of step i lives in slot i&1: after a speculation hit the chain warp goes straight on to
+    // byte i+1 and must not overwrite what the model threads are about to read
+    volatile u32* vbyte = reinterpret_cast<volatile u32*>(scode + 2048);
     cm_tables_init_smem(cm_smem);
     const int tid = threadIdx.x;
     if (tid < 32)
@@ -529,7 +554,7 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
                 ptab[((i + 1) & 1) * 256 + node] = (u32)(sse * 3 + (int)p_s) << 14;
             }
             __syncthreads();   // byte ready
-            const u32 byte = *vbyte;
+            const u32 byte = vbyte[i & 1];
             const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
             const bool one = ((byte >> (sh - 1)) & 1u) != 0;
             const u32 na = one ? a1 : a0, nb = one ? b1 : b0;
@@ -587,6 +612,18 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 u32 bit;
+#if defined(BZ_EMU)
+                {
+                    const u32 mid = flow + x;
+                    bit = code <= mid;
+                    frange = bit ? x : frange - x - 1u;
+                    pcur = bit ? kid1 : kid0;
+                    x = __umulhi(frange, pcur);
+                    if (!bit) flow = mid + 1u;
+                    const u32 t = flow ^ (flow + frange);
+                    tmin = t < tmin ? t : tmin;
+                }
+#else
                 asm volatile(
                     "{\n\t"
                     ".reg .pred pb;\n\t"
@@ -606,6 +643,7 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
                     "}"
                     : "+r"(flow), "+r"(frange), "+r"(x), "+r"(pcur), "=r"(bit), "+r"(tmin)
                     : "r"(code), "r"(kid0), "r"(kid1));
+#endif
                 node = node * 2 + bit;
                 kid0 = bit ? gk.z : gk.x;
                 kid1 = bit ? gk.w : gk.y;
@@ -625,6 +663,17 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     u32 bit, slow;
+#if defined(BZ_EMU)
+                    {
+                        const u32 mid = low + x;
+                        bit = code <= mid;
+                        range = bit ? x : range - x - 1u;
+                        pcur = bit ? kid1 : kid0;
+                        x = __umulhi(range, pcur);
+                        if (!bit) low = mid + 1u;
+                        slow = range < 0x1000000u;
+                    }
+#else
                     asm volatile(
                         "{\n\t"
                         ".reg .pred pb, ps;\n\t"
@@ -643,6 +692,7 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
                         "}"
                         : "+r"(low), "+r"(range), "+r"(x), "+r"(pcur), "=r"(bit), "=r"(slow)
                         : "r"(code), "r"(kid0), "r"(kid1));
+#endif
                     node = node * 2 + bit;
                     kid0 = bit ? gk.z : gk.x;
                     kid1 = bit ? gk.w : gk.y;
@@ -664,7 +714,7 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         }
         const u32 byte = node & 255u;
         // every lane holds the same byte: unconditional (convergent) stores of one value to one address
-        *vbyte = byte;
+        vbyte[i & 1] = byte;
         out[i] = (u8)byte;
         if (ip - wlo >= 1024) {  // uniform in the warp; the window belongs to this warp alone
             __syncwarp();
@@ -695,7 +745,7 @@ constexpr int kCmDecPathsThreads = 256;
 
 __global__ void __launch_bounds__(kCmDecPathsThreads) cm_decode_paths_kernel(const u8* __restrict__ in, s32 insize,
                                                                             u8* __restrict__ out, s32 n) {
-    extern __shared__ __align__(16) u16 cm_smem[];
+    BZ_DYN_SMEM(u16, cm_smem);
     u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [256]  P << 14 per node
     u8* scode = reinterpret_cast<u8*>(ptab + 256);              // [2048] window of the compressed stream
     volatile u32* st = reinterpret_cast<volatile u32*>(scode + 2048);  // 2 slots of 8: [0]=byte [1]=low [2]=range [3]=code [4]=ip
@@ -855,6 +905,7 @@ __global__ void __launch_bounds__(kCmDecPathsThreads) cm_decode_paths_kernel(con
     }
 }
 
+#if defined(__CUDACC__)
 inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
@@ -864,7 +915,8 @@ inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     return cudaSuccess;
 }
+#endif
 
-#endif  // __CUDACC__
+#endif  // BZ_DEVICE_CODE
 
 }  // namespace bz3

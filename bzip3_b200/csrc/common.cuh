@@ -8,9 +8,19 @@
 #include <cuda_runtime.h>
 #define BZ_HD __host__ __device__ __forceinline__
 #define BZ_D __device__ __forceinline__
+#define BZ_DEVICE_CODE 1
+// dynamic shared memory of a kernel, and a hint inside spin-waits (both have a CPU-emulator meaning, below)
+#define BZ_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define BZ_SPIN_HINT()
 #else
 #define BZ_HD inline
 #define BZ_D inline
+// BZ_EMU: the CPU test-suite compiles the kernel bodies with g++ on top of tests/native/cta_emu.h (one
+// fiber per CUDA thread), which must be included first and supplies the CUDA vocabulary.  Inline PTX has
+// a plain C++ twin under BZ_EMU.  Test infrastructure only -- the library itself is always built by nvcc.
+#if defined(BZ_EMU)
+#define BZ_DEVICE_CODE 1
+#endif
 #endif
 
 typedef uint8_t u8;
@@ -33,7 +43,6 @@ constexpr u32 kCrcPoly = 0x82F63B78u;  // reflected CRC-32C polynomial (src/libb
 BZ_HD size_t block_bound(size_t n) { return n + n / 50 + 32; }  // src/libbz3.c:510
 
 #if defined(__CUDACC__)
-
 #define BZ_CUDA_TRY(expr)                                                                         \
     do {                                                                                          \
         cudaError_t _e = (expr);                                                                  \
@@ -44,21 +53,28 @@ BZ_HD size_t block_bound(size_t n) { return n + n / 50 + 32; }  // src/libbz3.c:
         }                                                                                         \
     } while (0)
 
-constexpr u32 kFullMask = 0xFFFFFFFFu;
-
 // every kernel launch of the library is counted per host thread (bench.py reports it as gpu_launches)
 inline u64& launch_counter() {
     static thread_local u64 c = 0;
     return c;
 }
 #define BZ_NOTE_LAUNCH() (++::bz3::launch_counter())
+#endif  // __CUDACC__
+
+#if defined(BZ_DEVICE_CODE)
+
+constexpr u32 kFullMask = 0xFFFFFFFFu;
 
 BZ_D u32 lane_id() { return threadIdx.x & 31; }
 BZ_D u32 warp_id() { return threadIdx.x >> 5; }
 BZ_D u32 lanemask_lt() {
+#if defined(BZ_EMU)
+    return (1u << (threadIdx.x & 31)) - 1u;
+#else
     u32 m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+#endif
 }
 
 template <typename T>
@@ -80,13 +96,17 @@ BZ_D u32 warp_scan_incl(u32 v) {
 
 // streaming 128-bit load that does not pollute L1 (guide: Guideline 13)
 BZ_D uint4 ld_stream_u4(const uint4* p) {
+#if defined(BZ_EMU)
+    return *p;
+#else
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+#endif
 }
 
-#endif  // __CUDACC__
+#endif  // BZ_DEVICE_CODE
 
 }  // namespace bz3

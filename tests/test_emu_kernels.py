@@ -1,0 +1,159 @@
+"""CPU execution of the real CUDA kernel bodies (bzip3_b200/csrc/cm.cuh, lzp_parallel.cuh) on the
+thread-block emulator of tests/native/cta_emu.h, compared bit-for-bit with the oracle.
+
+This is the "no GPU in this container" safety net for the warp-/CTA-cooperative kernels: every CUDA thread
+is a fiber, barriers and warp collectives are the switch points (see cta_emu.h for the limits: it proves
+the protocol and the arithmetic, not the absence of races and nothing about speed).  The GPU parity tests
+in test_gpu_parity.py remain the real gate."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bzip3_b200 import synth
+from tests import refs
+
+ROOT = refs.ROOT
+SO = os.path.join(ROOT, "tests", "_build", "libemucheck.so")
+SRCS = [os.path.join(ROOT, "tests", "native", f) for f in ("emu_check.cpp", "cta_emu.cpp")]
+DEPS = SRCS + [os.path.join(ROOT, "tests", "native", "cta_emu.h")] + [
+    os.path.join(ROOT, "bzip3_b200", "csrc", f) for f in ("common.cuh", "cm.cuh", "lzp.cuh", "lzp_parallel.cuh")]
+
+_lib = None
+
+
+def emu():
+    global _lib
+    if _lib is None:
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-x", "c++",
+                                   "-o", SO] + SRCS)
+        L = C.CDLL(SO)
+        L.emu_set_schedule.argtypes = [C.c_int, C.c_ulonglong]
+        L.emu_cm_encode.restype = C.c_int32
+        L.emu_cm_encode.argtypes = [C.c_int, refs.u8p, C.c_int32, refs.u8p]
+        L.emu_cm_decode.restype = C.c_int
+        L.emu_cm_decode.argtypes = [C.c_int, refs.u8p, C.c_int32, refs.u8p, C.c_int32]
+        L.emu_lzp_encode.restype = C.c_int32
+        L.emu_lzp_encode.argtypes = [refs.u8p, C.c_int32, refs.u8p, refs.i32p]
+        L.emu_lzp_decode.restype = C.c_int32
+        L.emu_lzp_decode.argtypes = [refs.u8p, C.c_int32, refs.u8p, C.c_int32, refs.i32p]
+        _lib = L
+    return _lib
+
+
+def arr(b):
+    return np.frombuffer(bytes(b), dtype=np.uint8).copy()
+
+
+def bwt_of(data: np.ndarray) -> np.ndarray:
+    """What the entropy stage really sees: the BWT of the data (oracle)."""
+    O = refs.oracle()
+    n = len(data)
+    out = np.zeros(n + 16, np.uint8)
+    O.orc_bwt(refs.ptr(data), refs.ptr(out), n)
+    return out[:n].copy()
+
+
+def cm_inputs():
+    rng = np.random.default_rng(99)
+    cases = [(name, arr(d)[:3000]) for name, d in synth.edge_cases() if len(d) > 0]
+    cases.append(("bwt_zipf_48k", bwt_of(synth.zipf_text(48 << 10, seed=7))))
+    cases.append(("bwt_source_32k", bwt_of(synth.source_corpus(32 << 10, seed=8))))
+    cases.append(("random_6k", rng.integers(0, 256, 6000, dtype=np.uint8)))
+    cases.append(("runs_20k", np.repeat(rng.integers(0, 4, 200, dtype=np.uint8), 100)))
+    cases.append(("one_byte", np.array([65], np.uint8)))
+    return cases
+
+
+CM_CASES = cm_inputs()
+CM_IDS = [c[0] for c in CM_CASES]
+
+ENC_VARIANTS = [0, 1, 2]
+DEC_VARIANTS = [0, 1, 3]
+
+
+@pytest.mark.parametrize("variant", ENC_VARIANTS)
+@pytest.mark.parametrize("name,data", CM_CASES, ids=CM_IDS)
+def test_cm_encode_kernels(name, data, variant):
+    E, O = emu(), refs.oracle()
+    n = len(data)
+    want = np.zeros(2 * n + 64, np.uint8)
+    got = np.zeros(2 * n + 64, np.uint8)
+    rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
+    rg = E.emu_cm_encode(variant, refs.ptr(data), n, refs.ptr(got))
+    assert rg == rw
+    assert bytes(got[:rg]) == bytes(want[:rw])
+
+
+@pytest.mark.parametrize("variant", DEC_VARIANTS)
+@pytest.mark.parametrize("name,data", CM_CASES, ids=CM_IDS)
+def test_cm_decode_kernels(name, data, variant):
+    E, O = emu(), refs.oracle()
+    n = len(data)
+    enc = np.zeros(2 * n + 64, np.uint8)
+    r = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(enc))
+    # the whole stream, a truncated stream (read_in() past the end adds -1) and an empty one
+    for insize in (r, max(r - 3, 0), r // 2, 0):
+        want = np.zeros(n + 8, np.uint8)
+        got = np.zeros(n + 8, np.uint8)
+        O.orc_cm_decode(refs.ptr(enc), insize, refs.ptr(want), n)
+        assert E.emu_cm_decode(variant, refs.ptr(enc), insize, refs.ptr(got), n) == 0
+        assert bytes(got[:n]) == bytes(want[:n]), (insize, r)
+        if insize == r:
+            assert bytes(got[:n]) == bytes(data)
+
+
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_cm_kernels_other_schedules(schedule):
+    """Same result when the fibers are scheduled in descending or pseudo-random order."""
+    E, O = emu(), refs.oracle()
+    data = CM_CASES[CM_IDS.index("bwt_zipf_48k")][1][:12000]
+    n = len(data)
+    want = np.zeros(2 * n + 64, np.uint8)
+    rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
+    E.emu_set_schedule(schedule, 4242)
+    try:
+        for v in ENC_VARIANTS:
+            got = np.zeros(2 * n + 64, np.uint8)
+            assert E.emu_cm_encode(v, refs.ptr(data), n, refs.ptr(got)) == rw
+            assert bytes(got[:rw]) == bytes(want[:rw])
+        for v in DEC_VARIANTS:
+            back = np.zeros(n + 8, np.uint8)
+            E.emu_cm_decode(v, refs.ptr(want), rw, refs.ptr(back), n)
+            assert bytes(back[:n]) == bytes(data)
+    finally:
+        E.emu_set_schedule(0, 1)
+
+
+LZP_CASES = [(name, arr(d)) for name, d in synth.edge_cases()] + [
+    ("source_96k", synth.source_corpus(96 << 10, seed=21)), ("log_64k", synth.log_stream(64 << 10, seed=22))]
+
+
+@pytest.mark.parametrize("name,data", LZP_CASES, ids=[c[0] for c in LZP_CASES])
+def test_lzp_warp_kernels(name, data):
+    E, O = emu(), refs.oracle()
+    n = len(data)
+    pad = np.zeros(n + 64, np.uint8)
+    pad[:n] = data
+    want = np.zeros(n + 64, np.uint8)
+    got = np.zeros(n + 64, np.uint8)
+    lut = np.zeros(1 << 18, np.int32)
+    lp = lut.ctypes.data_as(refs.i32p)
+    rw = O.orc_lzp_encode(refs.ptr(pad), n, refs.ptr(want), lp)
+    rg = E.emu_lzp_encode(refs.ptr(pad), n, refs.ptr(got), lp)
+    assert rg == rw
+    if rw > 0:
+        assert bytes(got[:rg]) == bytes(want[:rw])
+        for cut in (rw, rw - 1, rw // 2, 4, 3):
+            cap = refs.bound(n)
+            dw = np.zeros(cap + 64, np.uint8)
+            dg = np.zeros(cap + 64, np.uint8)
+            sw = O.orc_lzp_decode(refs.ptr(want), cut, refs.ptr(dw), cap, lp)
+            sg = E.emu_lzp_decode(refs.ptr(want), cut, refs.ptr(dg), cap, lp)
+            assert sg == sw, (cut, sg, sw)
+            if sw > 0:
+                assert bytes(dg[:sg]) == bytes(dw[:sw])
