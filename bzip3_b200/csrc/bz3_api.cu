@@ -82,6 +82,7 @@ struct bz3_state {
     s32 sort_rounds;
     double sort_ms;
     int variant[BZ3_STAGE_COUNT];
+    int cm_enc, cm_dec;   // entropy-stage kernel selection (see kCmEncDefault / kCmDecDefault)
     cudaEvent_t sort_ev[2 * 40];
 };
 
@@ -252,12 +253,27 @@ cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, i
     return unbwt(s->stream, d_in, n, idx, d_out, B, status);
 }
 
+// Entropy-stage kernels.  Encoder: 0 chunked pipeline with the select/mul.hi coder lane, 1 single lane
+// (cross-check), 2 chunked with the whole-byte exact tier (cross-check), 4 chunked with the one-multiply
+// coder lane.  Decoder: 0 tree kernel with a serial chain warp, 1 single lane, 3 all-paths (first edition),
+// 4 tree kernel with the lane-parallel chain warp, 5 all-paths with one multiply per level.
+// Defaults can be overridden per process with BZ3_B200_CM_ENC / BZ3_B200_CM_DEC (tuning, tests).
+constexpr int kCmEncDefault = 0;
+constexpr int kCmDecDefault = 0;
+
+int env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : fallback;
+}
+
 cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* out_size) {
     s32* d_res = reinterpret_cast<s32*>(s->d_scal + 12);
-    if (s->variant[BZ3_STAGE_CM] == 1)
+    if (s->cm_enc == 1)
         cm_encode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
-    else if (s->variant[BZ3_STAGE_CM] == 2)
+    else if (s->cm_enc == 2)
         cm_encode_chunked_kernel<1><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+    else if (s->cm_enc == 4)
+        cm_encode_chunked_kernel<2><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     else
         cm_encode_chunked_kernel<0><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     BZ_NOTE_LAUNCH();
@@ -269,10 +285,14 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
 }
 
 cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s32 n) {
-    if (s->variant[BZ3_STAGE_CM] == 1)
+    if (s->cm_dec == 1)
         cm_decode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, insize, d_out, n);
-    else if (s->variant[BZ3_STAGE_CM] == 3)
+    else if (s->cm_dec == 3)
         cm_decode_paths_kernel<<<1, kCmDecPathsThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+    else if (s->cm_dec == 4)
+        cm_decode_lanes_kernel<<<1, kCmDecThreads, kCmDecLanesSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+    else if (s->cm_dec == 5)
+        cm_decode_paths2_kernel<<<1, kCmDecP2Threads, kCmDecP2SmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else
         cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     BZ_NOTE_LAUNCH();
@@ -468,6 +488,8 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     s->block_size = block_size;
     s->device = dev;
     s->last_error = BZ3_OK;
+    s->cm_enc = env_int("BZ3_B200_CM_ENC", kCmEncDefault);
+    s->cm_dec = env_int("BZ3_B200_CM_DEC", kCmDecDefault);
     const size_t n = block_bound((size_t)block_size) + 64;
     s->cap = align_up(n + 256);
     bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -830,6 +852,16 @@ extern "C" BZIP3_API void bz3_b200_debug_cm_profile(unsigned long long* out16) {
 #endif
 BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant) {
     if (stage >= 0 && stage < BZ3_STAGE_COUNT) s->variant[stage] = variant;
+    // the entropy stage has separate encoder / decoder selections: BZ3_STAGE_CM sets both (0 = defaults),
+    // BZ3_STAGE_CM + 100 the encoder alone, BZ3_STAGE_CM + 200 the decoder alone
+    if (stage == BZ3_STAGE_CM) {
+        s->cm_enc = variant ? variant : env_int("BZ3_B200_CM_ENC", kCmEncDefault);
+        s->cm_dec = variant ? variant : env_int("BZ3_B200_CM_DEC", kCmDecDefault);
+    } else if (stage == BZ3_STAGE_CM + 100) {
+        s->cm_enc = variant;
+    } else if (stage == BZ3_STAGE_CM + 200) {
+        s->cm_dec = variant;
+    }
 }
 
 // ------------------------------------------------------------------ single stages on host buffers (tests)

@@ -308,6 +308,59 @@ __device__ __noinline__ uint4 rc_exact_byte(u32 low, u32 range, s32 op, u32 sym,
     return make_uint4(low, high - low, (u32)op, 0u);
 }
 
+// 32 x 32 -> 64 bit product (one IMAD.WIDE): high half = new range, low half = exactness check
+BZ_D u64 cm_mul_wide(u32 a, u32 b) {
+#if defined(BZ_EMU)
+    return (u64)a * b;
+#else
+    u64 d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return d;
+#endif
+}
+
+// MODE 2 coder lane: one multiply per decision.  The SSE stage stored  m = bit ? M : -M  (M = P << 14), and
+//     bit 1:  new range = x = hi32(range * M)
+//     bit 0:  new range = range - x - 1 = hi32(range * -M)        unless lo32(range * M) == 0
+// so the recurrence is eight dependent IMAD.WIDE per byte; low moves by (range_k - range_{k+1}) at 0-bits.
+// Ranges only shrink, so "no decision of this byte needed a shift" is implied by  range_8 >= 2^24  (necessary
+// condition for a shift: range < 2^24); otherwise, or when a low half was zero, the byte is redone from its
+// start state by the reference loop.
+BZ_D void rc_byte2(u32& low, u32& range, s32& op, const u32 sym, const uint4 ca, const uint4 cb, u8* __restrict__ out) {
+    const u32 m[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+    u32 r = range, l = low, zmin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const u64 w = cm_mul_wide(r, m[k]);
+        const u32 rn = (u32)(w >> 32);
+        zmin = min(zmin, (u32)w);
+        if (!(sym & (0x80u >> k))) l += r - rn;
+        r = rn;
+    }
+    if (r >= (1u << 24) && zmin != 0u) {
+        low = l;
+        range = r;
+        return;
+    }
+    // exact tier (reference src/libbz3.c:388-416)
+    u32 high = low + range;
+    l = low;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const bool bit = (sym & (0x80u >> k)) != 0;
+        const u32 mk = bit ? m[k] : 0u - m[k];
+        const u32 x = __umulhi(high - l, mk);
+        if (bit) high = l + x; else l += x + 1u;
+        while ((l ^ high) < (1u << 24)) {
+            out[op++] = (u8)(l >> 24);
+            l <<= 8;
+            high = (high << 8) | 0xFFu;
+        }
+    }
+    low = l;
+    range = high - l;
+}
+
 // Three-stage chunk pipeline (one __syncthreads per chunk, no polling):
 //   warp 0, lanes 0..7  stage 1: c0 / c1 counters of tree depth `lane`  -> mixed probability p (16 bit)
 //   warp 2, lanes 0..7  stage 2: SSE rows c2 of depth `lane`            -> P << 14
@@ -383,7 +436,11 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                     u16* cell = c2 + (2 * node + flag) * 17 + (p >> 12);
                     const int lo = cell[0], hi = cell[1];
                     const int sse = lo + (((hi - lo) * (p & 4095)) >> 12);
-                    pb[k * 8] = (u32)(sse * 3 + p) << 14;
+                    {
+                        const u32 m = (u32)(sse * 3 + p) << 14;
+                        // MODE 2: the coder lane multiplies by M for a 1-bit and by -M for a 0-bit (see rc_fast_byte2)
+                        pb[k * 8] = (MODE == 2 && !ones) ? 0u - m : m;
+                    }
                     cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
                     cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
                     prev2 = prev1;
@@ -418,7 +475,9 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym) : "r"(sp));
 #endif
                     }
-                    if (MODE == 0) {
+                    if (MODE == 2) {
+                        rc_byte2(low, range, op, cs, ca, cb, out);
+                    } else if (MODE == 0) {
                         const u32 low0 = low, range0 = range, x0 = x;
                         u32 tmin = 0xFFFFFFFFu;
                         rc_fast_step(low, range, x, tmin, cs & 0x80u, ca.y);
@@ -468,6 +527,106 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
     }
 }
 
+// probability table of one byte step.  LAYOUT 0: u32 M = P << 14 per node (serial walk).  LAYOUT 1: {M, -M}
+// per node, so that a lane of the lane-parallel walk fetches the multiplier of ITS branch directly.
+template <int LAYOUT>
+BZ_D void cm_ptab_put(u32* ptab, int idx, u32 m) {
+    if (LAYOUT == 0) ptab[idx] = m;
+    else reinterpret_cast<uint2*>(ptab)[idx] = make_uint2(m, 0u - m);
+}
+
+// model thread of the tree decoders: owner of tree node `node` (0 is a dummy)
+template <int LAYOUT>
+BZ_D void cm_dec_model_thread(u16* cm_smem, u32* ptab, volatile u32* vbyte, s32 n, const int node) {
+    // ------------------------------------------------------------------ model thread
+    // Owns one node; its counters are carried in registers (only this thread writes them).  While the
+    // chain warp walks byte i the thread (1) computes both outcomes of its pending update and
+    // (2) SPECULATES that byte i repeats byte i-1 -- the common case in BWT output -- and predicts
+    // byte i+1 under that hypothesis into the other half of ptab.  On a hit the chain continues at
+    // once (no predict phase, no second barrier); on a miss the speculation is simply overwritten.
+    const int sh = node ? 8 - (31 - __clz(node)) : 8;                 // (256|byte) >> sh == node <=> on the path
+    u16* const q0 = cm_smem + node;
+    u16* const c1col = cm_smem + kCmC0 + node;                        // + prev * 256
+    u16* const rows = cm_smem + kCmC0 + kCmC1 + (2 * node) * 17;      // + flag * 17 + cell
+    int prev1 = 0, prev2 = 0;
+    u32 run = 0;
+    u16* q1 = c1col;
+    u32 a = *q0, b = *q1, d = *q1;
+    u32 lo = 0, hi = 0;
+    u16* cell = rows;
+    bool have = false;   // ptab of the current byte was already produced by the speculation
+    for (s32 i = 0; i < n; i++) {
+        if (!have) {
+            run = (prev1 == prev2) ? run + 1 : 0;
+            const int flag = run > 2;
+            // (A) predict byte i
+            const u32 p = ((a + b) * 7 + d + d) >> 4;
+            cell = rows + flag * 17 + (p >> 12);
+            lo = cell[0];
+            hi = cell[1];
+            const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
+            cm_ptab_put<LAYOUT>(ptab, (i & 1) * 256 + node, (u32)(sse * 3 + (int)p) << 14);   // slot 0 is never read
+            __syncthreads();   // ptab ready
+        }
+        // both outcomes of the update of byte i
+        const u32 a0 = cm_adapt_bf(a, 0u, 2), a1 = cm_adapt_bf(a, 0xFFFFu, 2);
+        const u32 b0 = cm_adapt_bf(b, 0u, 4), b1 = cm_adapt_bf(b, 0xFFFFu, 4);
+        const u32 l0 = cm_adapt_bf(lo, 0u, 6), l1 = cm_adapt_bf(lo, 0xFFFFu, 6);
+        const u32 h0 = cm_adapt_bf(hi, 0u, 6), h1 = cm_adapt_bf(hi, 0xFFFFu, 6);
+        // speculation: byte i == prev1.  Then prev1' = prev2' = prev1, both order-1 inputs of byte i+1 are
+        // this thread's current order-1 counter (updated if the node is on the path of prev1).
+        const u32 hyp = (u32)prev1;
+        const bool on_h = node != 0 && ((256u | hyp) >> sh) == (u32)node;
+        const bool one_h = ((hyp >> (sh - 1)) & 1u) != 0;
+        const u32 a_s = on_h ? (one_h ? a1 : a0) : a;
+        const u32 b_s = on_h ? (one_h ? b1 : b0) : b;
+        const u32 run_s = run + 1u;   // run rule (src/libbz3.c:367-370) applied to (prev1, prev1)
+        const int flag_s = run_s > 2;
+        const u32 p_s = ((a_s + b_s) * 7 + b_s + b_s) >> 4;
+        u16* const cell_s = rows + flag_s * 17 + (p_s >> 12);
+        u32 lo_s = cell_s[0], hi_s = cell_s[1];
+        {
+            const u32 nl = one_h ? l1 : l0, nh = one_h ? h1 : h0;   // what byte i would leave in cell[0], cell[1]
+            const bool same = on_h && cell_s == cell, up = on_h && cell_s == cell + 1, dn = on_h && cell_s + 1 == cell;
+            lo_s = same ? nl : (up ? nh : lo_s);
+            hi_s = same ? nh : (dn ? nl : hi_s);
+        }
+        {
+            const int sse = (int)lo_s + ((((int)hi_s - (int)lo_s) * (int)(p_s & 4095)) >> 12);
+            cm_ptab_put<LAYOUT>(ptab, ((i + 1) & 1) * 256 + node, (u32)(sse * 3 + (int)p_s) << 14);
+        }
+        __syncthreads();   // byte ready
+        const u32 byte = vbyte[i & 1];
+        const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
+        const bool one = ((byte >> (sh - 1)) & 1u) != 0;
+        const u32 na = one ? a1 : a0, nb = one ? b1 : b0;
+        if (on) {   // (C) learn byte i
+            *q0 = (u16)na;
+            *q1 = (u16)nb;
+            cell[0] = (u16)(one ? l1 : l0);
+            cell[1] = (u16)(one ? h1 : h0);
+        }
+        have = byte == hyp;   // uniform across the CTA
+        if (have) {
+            a = a_s;
+            b = b_s;
+            d = b_s;
+            lo = lo_s;
+            hi = hi_s;
+            cell = cell_s;
+            run = run_s;
+            prev2 = prev1;   // == byte
+        } else {
+            a = on ? na : a;
+            d = on ? nb : b;              // this byte's order-1 counter is the next byte's prev2 counter
+            prev2 = prev1;
+            prev1 = (int)byte;
+            q1 = c1col + prev1 * 256;
+            b = *q1;                      // after the store above in program order
+        }
+    }
+}
+
 // ---- tree-parallel decoder ---------------------------------------------------------------------
 // Decoding is one dependent chain: the next context depends on the bit just decoded.  What does not
 // depend on the bits of the current byte is the probability of every one of the 255 tree nodes (no node
@@ -495,94 +654,7 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         for (int k = tid; k < 2048; k += 32) scode[k] = (k < insize) ? in[k] : 0;
     __syncthreads();
     if (tid >= 32) {
-        // ------------------------------------------------------------------ model thread
-        // Owns one node; its counters are carried in registers (only this thread writes them).  While the
-        // chain warp walks byte i the thread (1) computes both outcomes of its pending update and
-        // (2) SPECULATES that byte i repeats byte i-1 -- the common case in BWT output -- and predicts
-        // byte i+1 under that hypothesis into the other half of ptab.  On a hit the chain continues at
-        // once (no predict phase, no second barrier); on a miss the speculation is simply overwritten.
-        const int node = tid - 32;                                        // 0 is a dummy
-        const int sh = node ? 8 - (31 - __clz(node)) : 8;                 // (256|byte) >> sh == node <=> on the path
-        u16* const q0 = cm_smem + node;
-        u16* const c1col = cm_smem + kCmC0 + node;                        // + prev * 256
-        u16* const rows = cm_smem + kCmC0 + kCmC1 + (2 * node) * 17;      // + flag * 17 + cell
-        int prev1 = 0, prev2 = 0;
-        u32 run = 0;
-        u16* q1 = c1col;
-        u32 a = *q0, b = *q1, d = *q1;
-        u32 lo = 0, hi = 0;
-        u16* cell = rows;
-        bool have = false;   // ptab of the current byte was already produced by the speculation
-        for (s32 i = 0; i < n; i++) {
-            if (!have) {
-                run = (prev1 == prev2) ? run + 1 : 0;
-                const int flag = run > 2;
-                // (A) predict byte i
-                const u32 p = ((a + b) * 7 + d + d) >> 4;
-                cell = rows + flag * 17 + (p >> 12);
-                lo = cell[0];
-                hi = cell[1];
-                const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
-                ptab[(i & 1) * 256 + node] = (u32)(sse * 3 + (int)p) << 14;   // slot 0 is never read
-                __syncthreads();   // ptab ready
-            }
-            // both outcomes of the update of byte i
-            const u32 a0 = cm_adapt_bf(a, 0u, 2), a1 = cm_adapt_bf(a, 0xFFFFu, 2);
-            const u32 b0 = cm_adapt_bf(b, 0u, 4), b1 = cm_adapt_bf(b, 0xFFFFu, 4);
-            const u32 l0 = cm_adapt_bf(lo, 0u, 6), l1 = cm_adapt_bf(lo, 0xFFFFu, 6);
-            const u32 h0 = cm_adapt_bf(hi, 0u, 6), h1 = cm_adapt_bf(hi, 0xFFFFu, 6);
-            // speculation: byte i == prev1.  Then prev1' = prev2' = prev1, both order-1 inputs of byte i+1 are
-            // this thread's current order-1 counter (updated if the node is on the path of prev1).
-            const u32 hyp = (u32)prev1;
-            const bool on_h = node != 0 && ((256u | hyp) >> sh) == (u32)node;
-            const bool one_h = ((hyp >> (sh - 1)) & 1u) != 0;
-            const u32 a_s = on_h ? (one_h ? a1 : a0) : a;
-            const u32 b_s = on_h ? (one_h ? b1 : b0) : b;
-            const u32 run_s = run + 1u;   // run rule (src/libbz3.c:367-370) applied to (prev1, prev1)
-            const int flag_s = run_s > 2;
-            const u32 p_s = ((a_s + b_s) * 7 + b_s + b_s) >> 4;
-            u16* const cell_s = rows + flag_s * 17 + (p_s >> 12);
-            u32 lo_s = cell_s[0], hi_s = cell_s[1];
-            {
-                const u32 nl = one_h ? l1 : l0, nh = one_h ? h1 : h0;   // what byte i would leave in cell[0], cell[1]
-                const bool same = on_h && cell_s == cell, up = on_h && cell_s == cell + 1, dn = on_h && cell_s + 1 == cell;
-                lo_s = same ? nl : (up ? nh : lo_s);
-                hi_s = same ? nh : (dn ? nl : hi_s);
-            }
-            {
-                const int sse = (int)lo_s + ((((int)hi_s - (int)lo_s) * (int)(p_s & 4095)) >> 12);
-                ptab[((i + 1) & 1) * 256 + node] = (u32)(sse * 3 + (int)p_s) << 14;
-            }
-            __syncthreads();   // byte ready
-            const u32 byte = vbyte[i & 1];
-            const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
-            const bool one = ((byte >> (sh - 1)) & 1u) != 0;
-            const u32 na = one ? a1 : a0, nb = one ? b1 : b0;
-            if (on) {   // (C) learn byte i
-                *q0 = (u16)na;
-                *q1 = (u16)nb;
-                cell[0] = (u16)(one ? l1 : l0);
-                cell[1] = (u16)(one ? h1 : h0);
-            }
-            have = byte == hyp;   // uniform across the CTA
-            if (have) {
-                a = a_s;
-                b = b_s;
-                d = b_s;
-                lo = lo_s;
-                hi = hi_s;
-                cell = cell_s;
-                run = run_s;
-                prev2 = prev1;   // == byte
-            } else {
-                a = on ? na : a;
-                d = on ? nb : b;              // this byte's order-1 counter is the next byte's prev2 counter
-                prev2 = prev1;
-                prev1 = (int)byte;
-                q1 = c1col + prev1 * 256;
-                b = *q1;                      // after the store above in program order
-            }
-        }
+        cm_dec_model_thread<0>(cm_smem, ptab, vbyte, n, tid - 32);
         return;
     }
     // ---------------------------------------------------------------------- chain warp (all lanes identical)
@@ -729,6 +801,266 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
         have = byte == prevb;
         prevb = byte;
     }
+}
+
+// ---- lane-parallel walk (variant 4) -------------------------------------------------------------------
+// The chain warp of the tree decoder executes every instruction for 32 lanes that all hold the same
+// values.  Here the lanes hold the 32 possible five-bit prefixes of the byte instead.  A lane's branches
+// are fixed, so its walk needs no compare/select/lookup chain -- one multiply per level:
+//     bit 1:  new range = x = (range * P) >> 18         = hi32(range * M),    M = P << 14
+//     bit 0:  new range = range - x - 1                 = hi32(range * -M)    unless lo32(range * M) == 0
+// (range * (2^32 - M) = range * 2^32 - range * M, and floor of that over 2^32 is range - ceil(range*M / 2^32)).
+// The model threads store {M, -M} per node and a lane loads the one of its branch; a lane that meets a zero
+// low half anywhere disqualifies itself (about once per 2^18 decisions; that also covers range == 0).
+// Without a renormalisation the 32 sub-intervals partition the current interval, so exactly one lane ends
+// with  code - low' <= range'  -- found with a ballot, its (low', range') broadcast with two shuffles.
+// low' needs no per-level work either: low only moves at 0-bits, by range_k - range_{k+1}, which telescopes
+// into a lane-constant +1/0/-1 combination of the ranges.  A second round does the last three levels with
+// 8 suffixes.  A lane whose range dropped below 2^24 (necessary for a shift) also disqualifies itself; if
+// that was the true path nobody wins and the round is redone by the reference loop (cm_dec_exact_levels).
+
+// reference loop for `nlev` tree levels from `node` on (src/libbz3.c:452-476); uniform across the warp
+BZ_D u32 cm_dec_exact_levels(const u32* __restrict__ pt, u32 node, const int nlev, u32& low, u32& range, u32& code,
+                             s32& ip, const s32 insize, const u8* __restrict__ scode) {
+    uint4 kids = *reinterpret_cast<const uint4*>(pt + 4 * node);   // children 2*node, 2*node+1: {M, -M, M, -M}
+    u32 m = pt[2 * node];
+    for (int k = 0; k < nlev; k++) {
+        const u32 x = __umulhi(range, m);
+        const u32 mid = low + x;
+        const bool bit = code <= mid;
+        range = bit ? x : range - x - 1u;
+        low = bit ? low : mid + 1u;
+        node = node * 2 + (bit ? 1u : 0u);
+        m = bit ? kids.z : kids.x;
+        if (node < 128) kids = *reinterpret_cast<const uint4*>(pt + 4 * node);
+        if (range < (1u << 24)) {   // necessary for the top bytes of low and high to agree
+            u32 high = low + range;
+            while ((low ^ high) < (1u << 24)) {
+                low <<= 8;
+                high = (high << 8) | 0xFFu;
+                const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;   // read_in() past the end adds -1
+                ip += (ip < insize);
+                code = (code << 8) + add;
+            }
+            range = high - low;
+        }
+    }
+    return node;
+}
+
+// Shared-memory access by 32-bit shared-window address with an immediate displacement (no generic-address
+// arithmetic in the loop).  The emulator keeps ordinary pointers.
+#if defined(BZ_EMU)
+typedef const u8* SmemAddr;
+BZ_D SmemAddr smem_addr_of(const volatile void* p) { return reinterpret_cast<const u8*>(const_cast<const void*>(p)); }
+template <int DISP> BZ_D u32 lds_u32(SmemAddr a) { return *reinterpret_cast<const volatile u32*>(a + DISP); }
+template <int DISP> BZ_D void sts_u32(SmemAddr a, u32 v) { *reinterpret_cast<volatile u32*>(const_cast<u8*>(a) + DISP) = v; }
+#else
+typedef u32 SmemAddr;
+BZ_D SmemAddr smem_addr_of(const volatile void* p) { return (u32)__cvta_generic_to_shared(const_cast<const void*>(p)); }
+template <int DISP> BZ_D u32 lds_u32(SmemAddr a) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(DISP) : "memory");
+    return v;
+}
+template <int DISP> BZ_D void sts_u32(SmemAddr a, u32 v) {
+    asm volatile("st.shared.u32 [%0+%1], %2;" :: "r"(a), "n"(DISP), "r"(v) : "memory");
+}
+#endif
+
+// ptxas likes to rematerialise thread-constant values from the thread id inside the hot loop (a dozen extra
+// instructions per byte).  Values that went through shared memory once are opaque to it and stay in registers.
+template <int N>
+BZ_D void launder_u32(u32 (&x)[N], volatile u32* scratch) {
+#pragma unroll
+    for (int k = 0; k < N; k++) scratch[k] = x[k];
+#pragma unroll
+    for (int k = 0; k < N; k++) x[k] = scratch[k];
+}
+
+#if defined(BZ_EMU_STATS)
+static unsigned long long g_emu_stats[8];
+#endif
+
+// One byte of the lane-parallel walk.  HALF (the parity of the byte index) is a template parameter so that
+// every shared-memory displacement in the loop is an immediate.
+struct CmLaneConsts {
+    SmemAddr a1[5];   // round 1: shared address of this lane's {M | -M} word at levels 0..4 (half 0)
+    SmemAddr a2[3];   // round 2: ptab base + the lane-constant part of the word offset at levels 5..7
+    u32 cs1[6];       // +1 / 0 / -1 (mod 2^32): coefficient of range_k in  low_5 - low_0
+    u32 cs2[4];
+};
+struct CmChainState {
+    u32 low, range, code, prevb;
+    s32 ip, wlo;
+    bool have;
+};
+
+template <int HALF>
+BZ_D void cm_dec_lanes_step(const CmLaneConsts& K, CmChainState& S, const s32 i, u32* ptab, const u8* __restrict__ scode,
+                            SmemAddr vbyte_a, const u8* __restrict__ in, const s32 insize, u8* __restrict__ out,
+                            const int tid) {
+    if (!S.have) __syncthreads();   // ptab ready (skipped when the speculation of the model threads hit)
+    constexpr int HB = HALF * 2048;   // byte offset of this byte's half of ptab
+    const u32* pt = ptab + HALF * 512;
+    u32 node;
+    {   // round 1: levels 0..4, 32 prefixes
+        const u32 m0 = lds_u32<HB>(K.a1[0]), m1 = lds_u32<HB>(K.a1[1]), m2 = lds_u32<HB>(K.a1[2]);
+        const u32 m3 = lds_u32<HB>(K.a1[3]), m4 = lds_u32<HB>(K.a1[4]);
+        const u64 w1 = cm_mul_wide(S.range, m0);
+        const u32 r1 = (u32)(w1 >> 32);
+        const u64 w2 = cm_mul_wide(r1, m1);
+        const u32 r2 = (u32)(w2 >> 32);
+        const u64 w3 = cm_mul_wide(r2, m2);
+        const u32 r3 = (u32)(w3 >> 32);
+        const u64 w4 = cm_mul_wide(r3, m3);
+        const u32 r4 = (u32)(w4 >> 32);
+        const u64 w5 = cm_mul_wide(r4, m4);
+        const u32 r5 = (u32)(w5 >> 32);
+        const u32 acc = K.cs1[0] * S.range + K.cs1[1] * r1 + K.cs1[2] * r2 + K.cs1[3] * r3 + K.cs1[4] * r4 + K.cs1[5] * r5;
+        const u32 zmin = min(min(min((u32)w1, (u32)w2), min((u32)w3, (u32)w4)), (u32)w5);   // 0 <=> some low half was 0
+        const u32 rchk = zmin ? r5 : 0u;   // ranges only shrink along a path: the last one is the smallest
+        const u32 d5 = S.code - S.low - acc;
+        const u32 win = __ballot_sync(kFullMask, d5 <= r5 && rchk >= (1u << 24));
+        if (win) {
+            const int w = 31 - __clz((int)win);   // exactly one lane wins
+            S.range = __shfl_sync(kFullMask, r5, w);
+            S.low = S.code - __shfl_sync(kFullMask, d5, w);
+            node = 32u | (u32)w;
+        } else {
+#if defined(BZ_EMU_STATS)
+            if (tid == 0) g_emu_stats[0]++;
+#endif
+            node = cm_dec_exact_levels(pt, 1u, 5, S.low, S.range, S.code, S.ip, insize, scode);
+        }
+    }
+    {   // round 2: levels 5..7, 8 suffixes (four copies each)
+        const u32 m5 = lds_u32<HB>(K.a2[0] + node * 8), m6 = lds_u32<HB>(K.a2[1] + node * 16), m7 = lds_u32<HB>(K.a2[2] + node * 32);
+        const u64 w6 = cm_mul_wide(S.range, m5);
+        const u32 r6 = (u32)(w6 >> 32);
+        const u64 w7 = cm_mul_wide(r6, m6);
+        const u32 r7 = (u32)(w7 >> 32);
+        const u64 w8 = cm_mul_wide(r7, m7);
+        const u32 r8 = (u32)(w8 >> 32);
+        const u32 acc = K.cs2[0] * S.range + K.cs2[1] * r6 + K.cs2[2] * r7 + K.cs2[3] * r8;
+        const u32 zmin = min(min((u32)w6, (u32)w7), (u32)w8);
+        const u32 rchk = zmin ? r8 : 0u;
+        const u32 d8 = S.code - S.low - acc;
+        const u32 win = __ballot_sync(kFullMask, d8 <= r8 && rchk >= (1u << 24));
+        if (win) {
+            const int w = (31 - __clz((int)win)) & 7;   // lanes j, j+8, j+16, j+24 hold suffix j
+            S.range = __shfl_sync(kFullMask, r8, w);
+            S.low = S.code - __shfl_sync(kFullMask, d8, w);
+            node = node * 8 + (u32)w;
+        } else {
+#if defined(BZ_EMU_STATS)
+            if (tid == 0) g_emu_stats[1]++;
+#endif
+            node = cm_dec_exact_levels(pt, node, 3, S.low, S.range, S.code, S.ip, insize, scode);
+        }
+    }
+    const u32 byte = node & 255u;
+    // every lane holds the same byte: unconditional (convergent) stores of one value to one address
+    sts_u32<HALF * 4>(vbyte_a, byte);
+    out[i] = (u8)byte;
+    if (S.ip - S.wlo >= 1024) {  // uniform in the warp; the window belongs to this warp alone
+        __syncwarp();
+        u8* sc = const_cast<u8*>(scode);
+        for (int k = tid; k < 1024; k += 32) {
+            const s32 src = S.wlo + 2048 + k;
+            sc[src & 2047] = (src < insize) ? in[src] : 0;
+        }
+        S.wlo += 1024;
+        __syncwarp();
+    }
+    __syncthreads();   // byte ready
+#if defined(BZ_EMU_STATS)
+    if (tid == 0) { g_emu_stats[2]++; g_emu_stats[3] += (byte == S.prevb); }
+#endif
+    S.have = byte == S.prevb;
+    S.prevb = byte;
+}
+
+BZ_D void cm_dec_lanes_chain(u32* ptab, u8* scode, volatile u32* vbyte, const u8* __restrict__ in, const s32 insize,
+                             u8* __restrict__ out, const s32 n) {
+    const int tid = threadIdx.x;
+    const u32 L = (u32)tid;
+    CmLaneConsts K;
+    {
+        // Round 1: the branch at level k is bit 4-k of the lane id.  Round 2: the branch at level 5+k is bit
+        // 2-k of j = lane & 7.  Word offset of a node's {M, -M} pair is 2*node; +1 selects -M (a 0-branch).
+        u32 zprev = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const u32 b = (L >> (4 - k)) & 1u;
+            const u32 nodek = (1u << k) | (L >> (5 - k));
+            K.a1[k] = smem_addr_of(ptab) + 4 * (nodek * 2 + (b ? 0u : 1u));
+            const u32 z = b ? 0u : 1u;
+            K.cs1[k] = z - zprev;
+            zprev = z;
+        }
+        K.cs1[5] = 0u - zprev;
+        const u32 j = L & 7u;
+        zprev = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const u32 b = (j >> (2 - k)) & 1u;
+            K.a2[k] = smem_addr_of(ptab) + 4 * ((j >> (3 - k)) * 2 + (b ? 0u : 1u));   // + (node << (3 + k)) at run time
+            const u32 z = b ? 0u : 1u;
+            K.cs2[k] = z - zprev;
+            zprev = z;
+        }
+        K.cs2[3] = 0u - zprev;
+    }
+    {
+        volatile u32* scr = vbyte + 16 + 32 * L;   // private scratch behind the byte slots
+#if !defined(BZ_EMU)
+        launder_u32(K.a1, scr);
+        launder_u32(K.a2, scr + 5);
+#endif
+        launder_u32(K.cs1, scr + 8);
+        launder_u32(K.cs2, scr + 14);
+    }
+    CmChainState S;
+    S.wlo = 0;  // the window holds stream bytes [wlo, wlo + 2048)
+    S.ip = 0;
+    S.low = 0;
+    S.range = 0xFFFFFFFFu;
+    S.code = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 add = (S.ip < insize) ? (u32)scode[S.ip & 2047] : 0xFFFFFFFFu;  // read_in() past the end adds -1
+        S.ip += (S.ip < insize);
+        S.code = (S.code << 8) + add;
+    }
+    S.have = false;
+    S.prevb = 0;
+    const SmemAddr vbyte_a = smem_addr_of(vbyte);
+    for (s32 i = 0; i < n; i += 2) {
+        cm_dec_lanes_step<0>(K, S, i, ptab, scode, vbyte_a, in, insize, out, tid);
+        if (i + 1 < n) cm_dec_lanes_step<1>(K, S, i + 1, ptab, scode, vbyte_a, in, insize, out, tid);
+    }
+}
+
+constexpr size_t kCmDecLanesSmemBytes = (size_t)kCmTableU16 * 2 + 2 * 256 * 8 + 2048 + 64 + 32 * 32 * 4;
+
+__global__ void __launch_bounds__(kCmDecThreads, 1) cm_decode_lanes_kernel(const u8* __restrict__ in, s32 insize,
+                                                                       u8* __restrict__ out, s32 n) {
+    BZ_DYN_SMEM(u16, cm_smem);
+    u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [2][256] {M, -M}; byte i uses half i&1
+    u8* scode = reinterpret_cast<u8*>(ptab + 1024);             // [2048] window of the compressed stream
+    volatile u32* vbyte = reinterpret_cast<volatile u32*>(scode + 2048);   // decoded byte of step i in slot i&1
+    cm_tables_init_smem(cm_smem);
+    const int tid = threadIdx.x;
+    if (tid < 32)
+        for (int k = tid; k < 2048; k += 32) scode[k] = (k < insize) ? in[k] : 0;
+    __syncthreads();
+    if (tid >= 32) {
+        cm_dec_model_thread<1>(cm_smem, ptab, vbyte, n, tid - 32);
+        return;
+    }
+    // ---------------------------------------------------------------------- chain warp
+    cm_dec_lanes_chain(ptab, scode, vbyte, in, insize, out, n);
 }
 
 // ---- all-paths decoder ---------------------------------------------------------------------------
@@ -905,14 +1237,173 @@ __global__ void __launch_bounds__(kCmDecPathsThreads) cm_decode_paths_kernel(con
     }
 }
 
+// ---- all-paths decoder, second edition (variant 5) ------------------------------------------------------
+// 256 threads, no chain warp.  Thread t owns tree node t (model role, as above) AND walks the root-to-leaf
+// path of byte value t with the one-multiply-per-level step of the lane-parallel walk: its eight branches
+// are fixed, so the walk is 8 shared loads at thread-constant addresses, 8 dependent IMAD.WIDE, one
+// lane-constant +1/0/-1 combination of the nine ranges for the new low, and one final test.  Without a
+// renormalisation the 256 leaf intervals partition the current interval: exactly one thread passes
+//   code - low' <= range'   and   range' >= 2^24   and   no zero low half on the way
+// and publishes (byte, low', range').  When the true path needs a shift nobody passes; the barrier
+// reduction reports that and thread 0 redoes the byte with the reference loop.  Per byte: predict -> barrier
+// -> walk -> barrier(+or) -> learn.  Every thread carries the (uniform) coder state in registers.
+constexpr int kCmDecP2Threads = 256;
+constexpr size_t kCmDecP2SmemBytes = (size_t)kCmTableU16 * 2 + 256 * 8 + 2048 + 64 + 256 * 20 * 4;
+
+__global__ void __launch_bounds__(kCmDecP2Threads, 1) cm_decode_paths2_kernel(const u8* __restrict__ in, s32 insize,
+                                                                          u8* __restrict__ out, s32 n) {
+    BZ_DYN_SMEM(u16, cm_smem);
+    u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [256] {M, -M} per node
+    u8* scode = reinterpret_cast<u8*>(ptab + 512);              // [2048] window of the compressed stream
+    volatile u32* pub = reinterpret_cast<volatile u32*>(scode + 2048);   // [0..3] byte, low, range, code  [4] ip
+    cm_tables_init_smem(cm_smem);
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 2048; k += kCmDecP2Threads) scode[k] = (k < insize) ? in[k] : 0;
+    // model role: owner of node `tid` (0 is a dummy)
+    const int node = tid;
+    const int sh = node ? 8 - (31 - __clz(node)) : 8;
+    u16* const q0 = cm_smem + node;
+    u16* const c1col = cm_smem + kCmC0 + node;
+    u16* const rows = cm_smem + kCmC0 + kCmC1 + (2 * node) * 17;
+    // path role: leaf v = tid.  Level k visits node (1 << k) | (v >> (8 - k)) and takes branch bit 7-k of v.
+    const u32 v = (u32)tid;
+    SmemAddr pa[8];
+    u32 cs[9];   // +1 / 0 / -1 (mod 2^32): coefficient of range_k in  low_8 - low_0
+    {
+        u32 zprev = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u32 b = (v >> (7 - k)) & 1u;
+            const u32 nodek = (1u << k) | (v >> (8 - k));
+            pa[k] = smem_addr_of(ptab) + 4 * (nodek * 2 + (b ? 0u : 1u));
+            const u32 z = b ? 0u : 1u;
+            cs[k] = z - zprev;
+            zprev = z;
+        }
+        cs[8] = 0u - zprev;
+    }
+    {
+        volatile u32* scr = pub + 16 + 20 * tid;   // private scratch behind the publication slots
+#if !defined(BZ_EMU)
+        launder_u32(pa, scr);
+#endif
+        launder_u32(cs, scr + 8);
+    }
+    const SmemAddr pub_a = smem_addr_of(pub);
+    __syncthreads();
+    int prev1 = 0, prev2 = 0;
+    u32 run = 0;
+    u16* q1 = c1col;
+    u32 a = *q0, b = *q1, d = *q1;
+    // coder state, identical in every thread
+    s32 wlo = 0, ip = 0;
+    u32 low = 0, range = 0xFFFFFFFFu, code = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;  // read_in() past the end adds -1
+        ip += (ip < insize);
+        code = (code << 8) + add;
+    }
+    for (s32 i = 0; i < n; i++) {
+        run = (prev1 == prev2) ? run + 1 : 0;
+        const int flag = run > 2;
+        // (A) predict byte i
+        const u32 p = ((a + b) * 7 + d + d) >> 4;
+        u16* const cell = rows + flag * 17 + (p >> 12);
+        const u32 lo = cell[0], hi = cell[1];
+        const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
+        cm_ptab_put<1>(ptab, node, (u32)(sse * 3 + (int)p) << 14);
+        __syncthreads();   // S1: ptab ready
+        // (B) walk my path
+        bool ok;
+        {
+            const u32 m0 = lds_u32<0>(pa[0]), m1 = lds_u32<0>(pa[1]), m2 = lds_u32<0>(pa[2]), m3 = lds_u32<0>(pa[3]);
+            const u32 m4 = lds_u32<0>(pa[4]), m5 = lds_u32<0>(pa[5]), m6 = lds_u32<0>(pa[6]), m7 = lds_u32<0>(pa[7]);
+            const u64 w1 = cm_mul_wide(range, m0);
+            const u32 r1 = (u32)(w1 >> 32);
+            const u64 w2 = cm_mul_wide(r1, m1);
+            const u32 r2 = (u32)(w2 >> 32);
+            const u64 w3 = cm_mul_wide(r2, m2);
+            const u32 r3 = (u32)(w3 >> 32);
+            const u64 w4 = cm_mul_wide(r3, m3);
+            const u32 r4 = (u32)(w4 >> 32);
+            const u64 w5 = cm_mul_wide(r4, m4);
+            const u32 r5 = (u32)(w5 >> 32);
+            const u64 w6 = cm_mul_wide(r5, m5);
+            const u32 r6 = (u32)(w6 >> 32);
+            const u64 w7 = cm_mul_wide(r6, m6);
+            const u32 r7 = (u32)(w7 >> 32);
+            const u64 w8 = cm_mul_wide(r7, m7);
+            const u32 r8 = (u32)(w8 >> 32);
+            const u32 acc = cs[0] * range + cs[1] * r1 + cs[2] * r2 + cs[3] * r3 + cs[4] * r4 + cs[5] * r5 + cs[6] * r6 +
+                            cs[7] * r7 + cs[8] * r8;
+            const u32 zmin = min(min(min((u32)w1, (u32)w2), min((u32)w3, (u32)w4)), min(min((u32)w5, (u32)w6), min((u32)w7, (u32)w8)));
+            const u32 d8 = code - low - acc;
+            ok = d8 <= r8 && zmin != 0u && r8 >= (1u << 24);   // ranges only shrink along a path: r8 is the smallest
+            if (ok) {
+                sts_u32<0>(pub_a, v);
+                sts_u32<4>(pub_a, code - d8);
+                sts_u32<8>(pub_a, r8);
+            }
+        }
+        const int won = __syncthreads_or(ok ? 1 : 0);   // S2: byte and state published (or nobody won)
+        if (!won) {
+            if (tid == 0) {   // exact serial decoder for this byte (reference loop)
+                u32 flow = low, frange = range, fcode = code;
+                s32 fip = ip;
+                const u32 nd = cm_dec_exact_levels(ptab, 1u, 8, flow, frange, fcode, fip, insize, scode);
+                pub[0] = nd & 255u;
+                pub[1] = flow;
+                pub[2] = frange;
+                pub[3] = fcode;
+                pub[4] = (u32)fip;
+            }
+            __syncthreads();
+            code = pub[3];
+            ip = (s32)pub[4];
+        }
+        const u32 byte = lds_u32<0>(pub_a);
+        low = lds_u32<4>(pub_a);
+        range = lds_u32<8>(pub_a);
+        if (tid == 0) out[i] = (u8)byte;
+        // (C) learn byte i
+        const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
+        const u32 ones = ((byte >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
+        const u32 na = cm_adapt_bf(a, ones, 2), nb = cm_adapt_bf(b, ones, 4);
+        if (on) {
+            *q0 = (u16)na;
+            *q1 = (u16)nb;
+            cell[0] = (u16)cm_adapt_bf(lo, ones, 6);
+            cell[1] = (u16)cm_adapt_bf(hi, ones, 6);
+        }
+        a = on ? na : a;
+        d = on ? nb : b;
+        prev2 = prev1;
+        prev1 = (int)byte;
+        q1 = c1col + prev1 * 256;
+        b = *q1;
+        // keep the stream window ahead of the read position (uniform)
+        if (ip - wlo >= 1024) {
+            for (int k = tid; k < 1024; k += kCmDecP2Threads) {
+                const s32 src = wlo + 2048 + k;
+                scode[src & 2047] = (src < insize) ? in[src] : 0;
+            }
+            wlo += 1024;
+        }
+    }
+}
+
 #if defined(__CUDACC__)
 inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecLanesSmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecP2SmemBytes));
     return cudaSuccess;
 }
 #endif

@@ -30,6 +30,10 @@ EXPORT int32_t emu_cm_encode(int variant, const uint8_t* in, int32_t n, uint8_t*
             b.x = kCmEncThreads;
             emu::launch(g, b, kCmEncSmemBytes, [&] { cm_encode_chunked_kernel<0>(in, n, out, &res); });
             break;
+        case 4:
+            b.x = kCmEncThreads;
+            emu::launch(g, b, kCmEncSmemBytes, [&] { cm_encode_chunked_kernel<2>(in, n, out, &res); });
+            break;
         default:
             return -777;
     }
@@ -50,6 +54,14 @@ EXPORT int emu_cm_decode(int variant, const uint8_t* in, int32_t insize, uint8_t
         case 0:
             b.x = kCmDecThreads;
             emu::launch(g, b, kCmDecSmemBytes, [&] { cm_decode_tree_kernel(in, insize, out, n); });
+            break;
+        case 4:
+            b.x = kCmDecThreads;
+            emu::launch(g, b, kCmDecLanesSmemBytes, [&] { cm_decode_lanes_kernel(in, insize, out, n); });
+            break;
+        case 5:
+            b.x = kCmDecP2Threads;
+            emu::launch(g, b, kCmDecP2SmemBytes, [&] { cm_decode_paths2_kernel(in, insize, out, n); });
             break;
         default:
             return -777;
