@@ -847,7 +847,7 @@ BZIP3_API void bz3_b200_last_sort_stats(struct bz3_state* s, uint64_t* records, 
 #ifdef BZ_CM_PROFILE
 extern "C" BZIP3_API void bz3_b200_debug_cm_profile(unsigned long long* out16) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out16, g_cm_prof, sizeof(unsigned long long) * 16);
+    cudaMemcpyFromSymbol(out16, g_cm_prof, sizeof(unsigned long long) * 48);
 }
 #endif
 BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant) {

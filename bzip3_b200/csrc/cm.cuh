@@ -179,7 +179,7 @@ BZ_D u32 cm_adapt_bf(u32 v, u32 ones /* bit ? 0xFFFF : 0 */, int rate) {
 }
 
 #ifdef BZ_CM_PROFILE
-__device__ unsigned long long g_cm_prof[16];
+__device__ unsigned long long g_cm_prof[48];
 #define BZ_PROF_DECL unsigned long long _t0 = clock64(), _t1
 #define BZ_PROF(slot) do { _t1 = clock64(); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
 // after a barrier: BAR.SYNC does not block at issue, so make the clock read depend on a post-barrier load
@@ -326,9 +326,15 @@ BZ_D u64 cm_mul_wide(u32 a, u32 b) {
 // Ranges only shrink, so "no decision of this byte needed a shift" is implied by  range_8 >= 2^24  (necessary
 // condition for a shift: range < 2^24); otherwise, or when a low half was zero, the byte is redone from its
 // start state by the reference loop.
-BZ_D void rc_byte2(u32& low, u32& range, s32& op, const u32 sym, const uint4 ca, const uint4 cb, u8* __restrict__ out) {
+BZ_D void rc_byte2(u32& low, u32& range, s32& op, const u32 sym, const uint4 ca, const uint4 cb, u8* __restrict__ out
+#ifdef BZ_CM_PROFILE
+                   , unsigned long long* _ex
+#endif
+) {
     const u32 m[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+    u32 rk[9];
     u32 r = range, l = low, zmin = 0xFFFFFFFFu;
+    rk[0] = r;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const u64 w = cm_mul_wide(r, m[k]);
@@ -336,12 +342,31 @@ BZ_D void rc_byte2(u32& low, u32& range, s32& op, const u32 sym, const uint4 ca,
         zmin = min(zmin, (u32)w);
         if (!(sym & (0x80u >> k))) l += r - rn;
         r = rn;
+        rk[k + 1] = rn;
     }
     if (r >= (1u << 24) && zmin != 0u) {
         low = l;
         range = r;
         return;
     }
+    if (zmin != 0u) {
+        // range < 2^24 is only necessary for a shift (low and high may straddle a top-byte boundary for a
+        // while): test the reference's condition after every decision before giving up on the fast result
+        u32 a = low, tmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (!(sym & (0x80u >> k))) a += rk[k] - rk[k + 1];
+            tmin = min(tmin, a ^ (a + rk[k + 1]));
+        }
+        if (tmin >= (1u << 24)) {
+            low = l;
+            range = r;
+            return;
+        }
+    }
+#ifdef BZ_CM_PROFILE
+    const unsigned long long _e0 = clock64();
+#endif
     // exact tier (reference src/libbz3.c:388-416)
     u32 high = low + range;
     l = low;
@@ -359,6 +384,10 @@ BZ_D void rc_byte2(u32& low, u32& range, s32& op, const u32 sym, const uint4 ca,
     }
     low = l;
     range = high - l;
+#ifdef BZ_CM_PROFILE
+    _ex[0] += clock64() - _e0;
+    _ex[1] += 1;
+#endif
 }
 
 // Three-stage chunk pipeline (one __syncthreads per chunk, no polling):
@@ -389,6 +418,7 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
     s32 op = 0;
 #ifdef BZ_CM_PROFILE
     unsigned long long _busy = 0;
+    unsigned long long _ex[2] = {0, 0};
 #endif
     for (s32 it = 0; it < nchunks + 2; it++) {
 #ifdef BZ_CM_PROFILE
@@ -476,7 +506,11 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
 #endif
                     }
                     if (MODE == 2) {
+#ifdef BZ_CM_PROFILE
+                        rc_byte2(low, range, op, cs, ca, cb, out, _ex);
+#else
                         rc_byte2(low, range, op, cs, ca, cb, out);
+#endif
                     } else if (MODE == 0) {
                         const u32 low0 = low, range0 = range, x0 = x;
                         u32 tmin = 0xFFFFFFFFu;
@@ -517,6 +551,10 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
     }
 #ifdef BZ_CM_PROFILE
     if (lane == 0) g_cm_prof[13 + (warp == 0 ? 0 : warp == 2 ? 1 : 2)] = _busy;   // stage1, stage2, coder
+    if (threadIdx.x == 32) {
+        g_cm_prof[32] = _ex[0];   // MODE 2: cycles and bytes in the exact tier of the coder lane
+        g_cm_prof[33] = _ex[1];
+    }
 #endif
     if (threadIdx.x == 32) {
         for (int k = 0; k < 4; k++) {  // flush (reference src/libbz3.c:425-432)
@@ -669,8 +707,12 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
     }
     bool have = false;
     u32 prevb = 0;
+#ifdef BZ_CM_PROFILE
+    unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, _t0 = clock64(), _t1;
+#endif
     for (s32 i = 0; i < n; i++) {
         if (!have) __syncthreads();   // ptab ready (skipped when the speculation of the model threads hit)
+        BZ_PROF_AFTER_BAR(0, ptab + (i & 1) * 256 + 1);
         const u32* pt = ptab + (i & 1) * 256;
         const uint4 g0 = *reinterpret_cast<const uint4*>(pt);
         uint4 gk = *reinterpret_cast<const uint4*>(pt + 4);
@@ -721,10 +763,14 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
                 kid1 = bit ? gk.w : gk.y;
                 if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
             }
+            BZ_PROF(1);
             if (tmin >= (1u << 24)) {
                 low = flow;
                 range = frange;
             } else {
+#ifdef BZ_CM_PROFILE
+                _acc[4]++;
+#endif
                 // exact tier: same walk, renormalising after every step like the reference
                 node = 1;
                 gk = *reinterpret_cast<const uint4*>(pt + 4);
@@ -784,6 +830,7 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
                 }
             }
         }
+        BZ_PROF(2);
         const u32 byte = node & 255u;
         // every lane holds the same byte: unconditional (convergent) stores of one value to one address
         vbyte[i & 1] = byte;
@@ -798,9 +845,14 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
             __syncwarp();
         }
         __syncthreads();   // byte ready
+        BZ_PROF_AFTER_BAR(3, ptab);
         have = byte == prevb;
         prevb = byte;
     }
+#ifdef BZ_CM_PROFILE
+    if (tid == 0)
+        for (int k = 0; k < 5; k++) g_cm_prof[8 + k] = _acc[k];   // wait ptab, fast tier, exact tier, publish+wait byte, #redo
+#endif
 }
 
 // ---- lane-parallel walk (variant 4) -------------------------------------------------------------------
@@ -889,18 +941,32 @@ struct CmLaneConsts {
     SmemAddr a2[3];   // round 2: ptab base + the lane-constant part of the word offset at levels 5..7
     u32 cs1[6];       // +1 / 0 / -1 (mod 2^32): coefficient of range_k in  low_5 - low_0
     u32 cs2[4];
+    u32 z1[5], z2[3]; // all-ones where this lane takes the 0-branch at that level (slow path only)
 };
 struct CmChainState {
     u32 low, range, code, prevb;
     s32 ip, wlo;
     bool have;
+#ifdef BZ_CM_PROFILE
+    unsigned long long _acc[8], _t0, _t1;
+#endif
 };
+#ifdef BZ_CM_PROFILE
+#define BZ_SPROF(S, slot) do { (S)._t1 = clock64(); (S)._acc[slot] += (S)._t1 - (S)._t0; (S)._t0 = (S)._t1; } while (0)
+#define BZ_SPROF_AFTER_BAR(S, slot, ptr) do { unsigned _v = *(ptr); asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"((S)._t1) : "r"(_v)); (S)._acc[slot] += (S)._t1 - (S)._t0; (S)._t0 = (S)._t1; } while (0)
+#define BZ_SCOUNT(S, slot) ((S)._acc[slot]++)
+#else
+#define BZ_SPROF(S, slot)
+#define BZ_SPROF_AFTER_BAR(S, slot, ptr)
+#define BZ_SCOUNT(S, slot)
+#endif
 
 template <int HALF>
 BZ_D void cm_dec_lanes_step(const CmLaneConsts& K, CmChainState& S, const s32 i, u32* ptab, const u8* __restrict__ scode,
                             SmemAddr vbyte_a, const u8* __restrict__ in, const s32 insize, u8* __restrict__ out,
                             const int tid) {
     if (!S.have) __syncthreads();   // ptab ready (skipped when the speculation of the model threads hit)
+    BZ_SPROF_AFTER_BAR(S, 0, ptab + HALF * 512 + 2);
     constexpr int HB = HALF * 2048;   // byte offset of this byte's half of ptab
     const u32* pt = ptab + HALF * 512;
     u32 node;
@@ -921,17 +987,37 @@ BZ_D void cm_dec_lanes_step(const CmLaneConsts& K, CmChainState& S, const s32 i,
         const u32 zmin = min(min(min((u32)w1, (u32)w2), min((u32)w3, (u32)w4)), (u32)w5);   // 0 <=> some low half was 0
         const u32 rchk = zmin ? r5 : 0u;   // ranges only shrink along a path: the last one is the smallest
         const u32 d5 = S.code - S.low - acc;
-        const u32 win = __ballot_sync(kFullMask, d5 <= r5 && rchk >= (1u << 24));
+        u32 win = __ballot_sync(kFullMask, d5 <= r5 && rchk >= (1u << 24));
+        if (!win) {
+            // range < 2^24 is only NECESSARY for a shift (low and high may straddle a top-byte boundary for a
+            // while).  Before giving up, every lane applies the reference's test to its own path.
+            u32 a = S.low, tmin;
+            a += K.z1[0] & (S.range - r1);
+            tmin = a ^ (a + r1);
+            a += K.z1[1] & (r1 - r2);
+            tmin = min(tmin, a ^ (a + r2));
+            a += K.z1[2] & (r2 - r3);
+            tmin = min(tmin, a ^ (a + r3));
+            a += K.z1[3] & (r3 - r4);
+            tmin = min(tmin, a ^ (a + r4));
+            a += K.z1[4] & (r4 - r5);
+            tmin = min(tmin, a ^ (a + r5));
+            win = __ballot_sync(kFullMask, d5 <= r5 && zmin != 0u && tmin >= (1u << 24));
+            BZ_SCOUNT(S, 6);
+        }
         if (win) {
             const int w = 31 - __clz((int)win);   // exactly one lane wins
             S.range = __shfl_sync(kFullMask, r5, w);
             S.low = S.code - __shfl_sync(kFullMask, d5, w);
             node = 32u | (u32)w;
+            BZ_SPROF(S, 1);
         } else {
+            BZ_SPROF(S, 1);
 #if defined(BZ_EMU_STATS)
             if (tid == 0) g_emu_stats[0]++;
 #endif
             node = cm_dec_exact_levels(pt, 1u, 5, S.low, S.range, S.code, S.ip, insize, scode);
+            BZ_SPROF(S, 2);
         }
     }
     {   // round 2: levels 5..7, 8 suffixes (four copies each)
@@ -946,17 +1032,31 @@ BZ_D void cm_dec_lanes_step(const CmLaneConsts& K, CmChainState& S, const s32 i,
         const u32 zmin = min(min((u32)w6, (u32)w7), (u32)w8);
         const u32 rchk = zmin ? r8 : 0u;
         const u32 d8 = S.code - S.low - acc;
-        const u32 win = __ballot_sync(kFullMask, d8 <= r8 && rchk >= (1u << 24));
+        u32 win = __ballot_sync(kFullMask, d8 <= r8 && rchk >= (1u << 24));
+        if (!win) {   // exact per-path shift test, as in round 1
+            u32 a = S.low, tmin;
+            a += K.z2[0] & (S.range - r6);
+            tmin = a ^ (a + r6);
+            a += K.z2[1] & (r6 - r7);
+            tmin = min(tmin, a ^ (a + r7));
+            a += K.z2[2] & (r7 - r8);
+            tmin = min(tmin, a ^ (a + r8));
+            win = __ballot_sync(kFullMask, d8 <= r8 && zmin != 0u && tmin >= (1u << 24));
+            BZ_SCOUNT(S, 7);
+        }
         if (win) {
             const int w = (31 - __clz((int)win)) & 7;   // lanes j, j+8, j+16, j+24 hold suffix j
             S.range = __shfl_sync(kFullMask, r8, w);
             S.low = S.code - __shfl_sync(kFullMask, d8, w);
             node = node * 8 + (u32)w;
+            BZ_SPROF(S, 3);
         } else {
+            BZ_SPROF(S, 3);
 #if defined(BZ_EMU_STATS)
             if (tid == 0) g_emu_stats[1]++;
 #endif
             node = cm_dec_exact_levels(pt, node, 3, S.low, S.range, S.code, S.ip, insize, scode);
+            BZ_SPROF(S, 4);
         }
     }
     const u32 byte = node & 255u;
@@ -974,6 +1074,7 @@ BZ_D void cm_dec_lanes_step(const CmLaneConsts& K, CmChainState& S, const s32 i,
         __syncwarp();
     }
     __syncthreads();   // byte ready
+    BZ_SPROF_AFTER_BAR(S, 5, ptab);
 #if defined(BZ_EMU_STATS)
     if (tid == 0) { g_emu_stats[2]++; g_emu_stats[3] += (byte == S.prevb); }
 #endif
@@ -995,6 +1096,7 @@ BZ_D void cm_dec_lanes_chain(u32* ptab, u8* scode, volatile u32* vbyte, const u8
             const u32 b = (L >> (4 - k)) & 1u;
             const u32 nodek = (1u << k) | (L >> (5 - k));
             K.a1[k] = smem_addr_of(ptab) + 4 * (nodek * 2 + (b ? 0u : 1u));
+            K.z1[k] = b ? 0u : 0xFFFFFFFFu;
             const u32 z = b ? 0u : 1u;
             K.cs1[k] = z - zprev;
             zprev = z;
@@ -1006,6 +1108,7 @@ BZ_D void cm_dec_lanes_chain(u32* ptab, u8* scode, volatile u32* vbyte, const u8
         for (int k = 0; k < 3; k++) {
             const u32 b = (j >> (2 - k)) & 1u;
             K.a2[k] = smem_addr_of(ptab) + 4 * ((j >> (3 - k)) * 2 + (b ? 0u : 1u));   // + (node << (3 + k)) at run time
+            K.z2[k] = b ? 0u : 0xFFFFFFFFu;
             const u32 z = b ? 0u : 1u;
             K.cs2[k] = z - zprev;
             zprev = z;
@@ -1036,10 +1139,18 @@ BZ_D void cm_dec_lanes_chain(u32* ptab, u8* scode, volatile u32* vbyte, const u8
     S.have = false;
     S.prevb = 0;
     const SmemAddr vbyte_a = smem_addr_of(vbyte);
+#ifdef BZ_CM_PROFILE
+    for (int k = 0; k < 8; k++) S._acc[k] = 0;
+    S._t0 = clock64();
+#endif
     for (s32 i = 0; i < n; i += 2) {
         cm_dec_lanes_step<0>(K, S, i, ptab, scode, vbyte_a, in, insize, out, tid);
         if (i + 1 < n) cm_dec_lanes_step<1>(K, S, i + 1, ptab, scode, vbyte_a, in, insize, out, tid);
     }
+#ifdef BZ_CM_PROFILE
+    if (tid == 0)
+        for (int k = 0; k < 8; k++) g_cm_prof[16 + k] = S._acc[k];   // wait ptab, r1 fast, r1 exact, r2 fast, r2 exact, publish+wait, #fb1, #fb2
+#endif
 }
 
 constexpr size_t kCmDecLanesSmemBytes = (size_t)kCmTableU16 * 2 + 2 * 256 * 8 + 2048 + 64 + 32 * 32 * 4;
@@ -1269,6 +1380,7 @@ __global__ void __launch_bounds__(kCmDecP2Threads, 1) cm_decode_paths2_kernel(co
     const u32 v = (u32)tid;
     SmemAddr pa[8];
     u32 cs[9];   // +1 / 0 / -1 (mod 2^32): coefficient of range_k in  low_8 - low_0
+    u32 zk[8];   // all-ones where this path takes the 0-branch (slow path only)
     {
         u32 zprev = 0;
 #pragma unroll
@@ -1276,6 +1388,7 @@ __global__ void __launch_bounds__(kCmDecP2Threads, 1) cm_decode_paths2_kernel(co
             const u32 b = (v >> (7 - k)) & 1u;
             const u32 nodek = (1u << k) | (v >> (8 - k));
             pa[k] = smem_addr_of(ptab) + 4 * (nodek * 2 + (b ? 0u : 1u));
+            zk[k] = b ? 0u : 0xFFFFFFFFu;
             const u32 z = b ? 0u : 1u;
             cs[k] = z - zprev;
             zprev = z;
@@ -1304,6 +1417,9 @@ __global__ void __launch_bounds__(kCmDecP2Threads, 1) cm_decode_paths2_kernel(co
         ip += (ip < insize);
         code = (code << 8) + add;
     }
+#ifdef BZ_CM_PROFILE
+    unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, _t0 = clock64(), _t1;
+#endif
     for (s32 i = 0; i < n; i++) {
         run = (prev1 == prev2) ? run + 1 : 0;
         const int flag = run > 2;
@@ -1313,54 +1429,81 @@ __global__ void __launch_bounds__(kCmDecP2Threads, 1) cm_decode_paths2_kernel(co
         const u32 lo = cell[0], hi = cell[1];
         const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
         cm_ptab_put<1>(ptab, node, (u32)(sse * 3 + (int)p) << 14);
+        BZ_PROF(0);
         __syncthreads();   // S1: ptab ready
+        BZ_PROF_AFTER_BAR(1, ptab + 2);
         // (B) walk my path
-        bool ok;
+        bool ok, ok2;
         {
             const u32 m0 = lds_u32<0>(pa[0]), m1 = lds_u32<0>(pa[1]), m2 = lds_u32<0>(pa[2]), m3 = lds_u32<0>(pa[3]);
             const u32 m4 = lds_u32<0>(pa[4]), m5 = lds_u32<0>(pa[5]), m6 = lds_u32<0>(pa[6]), m7 = lds_u32<0>(pa[7]);
-            const u64 w1 = cm_mul_wide(range, m0);
-            const u32 r1 = (u32)(w1 >> 32);
-            const u64 w2 = cm_mul_wide(r1, m1);
-            const u32 r2 = (u32)(w2 >> 32);
-            const u64 w3 = cm_mul_wide(r2, m2);
-            const u32 r3 = (u32)(w3 >> 32);
-            const u64 w4 = cm_mul_wide(r3, m3);
-            const u32 r4 = (u32)(w4 >> 32);
-            const u64 w5 = cm_mul_wide(r4, m4);
-            const u32 r5 = (u32)(w5 >> 32);
-            const u64 w6 = cm_mul_wide(r5, m5);
-            const u32 r6 = (u32)(w6 >> 32);
-            const u64 w7 = cm_mul_wide(r6, m6);
-            const u32 r7 = (u32)(w7 >> 32);
-            const u64 w8 = cm_mul_wide(r7, m7);
-            const u32 r8 = (u32)(w8 >> 32);
-            const u32 acc = cs[0] * range + cs[1] * r1 + cs[2] * r2 + cs[3] * r3 + cs[4] * r4 + cs[5] * r5 + cs[6] * r6 +
-                            cs[7] * r7 + cs[8] * r8;
-            const u32 zmin = min(min(min((u32)w1, (u32)w2), min((u32)w3, (u32)w4)), min(min((u32)w5, (u32)w6), min((u32)w7, (u32)w8)));
+            u32 rk[9];
+            u32 zmin = 0xFFFFFFFFu;
+            rk[0] = range;
+            const u32 mm[8] = {m0, m1, m2, m3, m4, m5, m6, m7};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const u64 w = cm_mul_wide(rk[k], mm[k]);
+                rk[k + 1] = (u32)(w >> 32);
+                zmin = min(zmin, (u32)w);
+            }
+            u32 acc = 0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) acc += cs[k] * rk[k];
+            const u32 r8 = rk[8];
             const u32 d8 = code - low - acc;
-            ok = d8 <= r8 && zmin != 0u && r8 >= (1u << 24);   // ranges only shrink along a path: r8 is the smallest
+            const bool cand = d8 <= r8 && zmin != 0u;
+            ok = cand && r8 >= (1u << 24);   // ranges only shrink along a path: r8 is the smallest
             if (ok) {
                 sts_u32<0>(pub_a, v);
                 sts_u32<4>(pub_a, code - d8);
                 sts_u32<8>(pub_a, r8);
             }
-        }
-        const int won = __syncthreads_or(ok ? 1 : 0);   // S2: byte and state published (or nobody won)
-        if (!won) {
-            if (tid == 0) {   // exact serial decoder for this byte (reference loop)
-                u32 flow = low, frange = range, fcode = code;
-                s32 fip = ip;
-                const u32 nd = cm_dec_exact_levels(ptab, 1u, 8, flow, frange, fcode, fip, insize, scode);
-                pub[0] = nd & 255u;
-                pub[1] = flow;
-                pub[2] = frange;
-                pub[3] = fcode;
-                pub[4] = (u32)fip;
+            BZ_PROF(2);
+            int won = __syncthreads_or(ok ? 1 : 0);   // S2: byte and state published (or nobody won)
+            BZ_PROF_AFTER_BAR(3, pub);
+            if (!won) {
+#ifdef BZ_CM_PROFILE
+                _acc[6]++;
+#endif
+                // range < 2^24 is only NECESSARY for a shift (low and high may straddle a top-byte boundary):
+                // every candidate applies the reference's test to its own path before the byte is redone serially
+                ok2 = false;
+                if (cand) {
+                    u32 al = low, tmin = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        al += zk[k] & (rk[k] - rk[k + 1]);
+                        tmin = min(tmin, al ^ (al + rk[k + 1]));
+                    }
+                    ok2 = tmin >= (1u << 24);
+                    if (ok2) {
+                        sts_u32<0>(pub_a, v);
+                        sts_u32<4>(pub_a, code - d8);
+                        sts_u32<8>(pub_a, r8);
+                    }
+                }
+                won = __syncthreads_or(ok2 ? 1 : 0);
+                if (!won) {
+#ifdef BZ_CM_PROFILE
+                    _acc[7]++;
+#endif
+                    if (tid == 0) {   // exact serial decoder for this byte (reference loop)
+                        u32 flow = low, frange = range, fcode = code;
+                        s32 fip = ip;
+                        const u32 nd = cm_dec_exact_levels(ptab, 1u, 8, flow, frange, fcode, fip, insize, scode);
+                        pub[0] = nd & 255u;
+                        pub[1] = flow;
+                        pub[2] = frange;
+                        pub[3] = fcode;
+                        pub[4] = (u32)fip;
+                    }
+                    __syncthreads();
+                    code = pub[3];
+                    ip = (s32)pub[4];
+                }
+                BZ_PROF_AFTER_BAR(4, pub);
             }
-            __syncthreads();
-            code = pub[3];
-            ip = (s32)pub[4];
         }
         const u32 byte = lds_u32<0>(pub_a);
         low = lds_u32<4>(pub_a);
@@ -1390,7 +1533,12 @@ __global__ void __launch_bounds__(kCmDecP2Threads, 1) cm_decode_paths2_kernel(co
             }
             wlo += 1024;
         }
+        BZ_PROF(5);
     }
+#ifdef BZ_CM_PROFILE
+    if (tid == 0)
+        for (int k = 0; k < 8; k++) g_cm_prof[24 + k] = _acc[k];   // predict, wait S1, walk, wait S2, fallback, learn, #slow, #serial
+#endif
 }
 
 #if defined(__CUDACC__)

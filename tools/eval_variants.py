@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     args = ap.parse_args()
     n = int(args.mib * (1 << 20))
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
     L = bzip3_b200.lib()
     O = refs.oracle()
     u8p = refs.u8p
@@ -42,6 +43,7 @@ def main():
             ("mixed", synth.mixed(n, seed=4244, segment=max(n // 4, 1 << 16)))]
     result = {"n": n, "sets": {}, "ok": True}
     with bzip3_b200.Bz3State(max(n, 1 << 20)) as st:
+        prep = {}
         for name, data in sets:
             data = np.ascontiguousarray(data[:n])
             bwt = np.zeros(n + 64, np.uint8)
@@ -55,49 +57,48 @@ def main():
             t0 = time.perf_counter()
             O.orc_cm_decode(want.ctypes.data_as(u8p), rw, back.ctypes.data_as(u8p), n)
             cpu_dec = time.perf_counter() - t0
-            rec = {"ratio": rw / n, "oracle_cpu_enc_MBps": n / cpu_enc / 1e6, "oracle_cpu_dec_MBps": n / cpu_dec / 1e6,
-                   "enc": {}, "dec": {}}
-            for v in ENC_VARIANTS:
-                L.bz3_b200_set_variant(st.handle, CM + 100, v)
+            cut = max(rw - 5, 0)
+            dw = np.zeros(n + 8, np.uint8)
+            O.orc_cm_decode(want.ctypes.data_as(u8p), cut, dw.ctypes.data_as(u8p), n)
+            prep[name] = (bwt, want, rw, cut, dw)
+            result["sets"][name] = {"ratio": rw / n, "oracle_cpu_enc_MBps": n / cpu_enc / 1e6,
+                                    "oracle_cpu_dec_MBps": n / cpu_dec / 1e6, "enc": {}, "dec": {}}
+            print("%s: ratio %.3f, oracle on one host core: enc %.1f MB/s, dec %.1f MB/s" % (
+                name, rw / n, n / cpu_enc / 1e6, n / cpu_dec / 1e6), flush=True)
+        # known-good kernels first, so that a fault in a new one cannot hide the baseline
+        order = [("enc", 0), ("dec", 0), ("enc", 4), ("dec", 5), ("dec", 4)]
+        for kind, v in order:
+            for name, _ in sets:
+                bwt, want, rw, cut, dw = prep[name]
                 best, ok = 1e9, True
-                for _ in range(args.reps):
-                    got = np.zeros(2 * n + 64, np.uint8)
-                    t0 = time.perf_counter()
-                    rg = L.bz3_b200_stage_cm_encode(st.handle, bwt.ctypes.data_as(u8p), n, got.ctypes.data_as(u8p))
-                    best = min(best, time.perf_counter() - t0)
-                    ok = ok and rg == rw and bytes(got[:rw]) == bytes(want[:rw])
-                rec["enc"][v] = {"ok": bool(ok), "ms": best * 1e3, "MBps": n / best / 1e6,
-                                 "cycles_per_byte_at_1.965GHz": best * 1.965e9 / n}
-                result["ok"] = result["ok"] and ok
-            L.bz3_b200_set_variant(st.handle, CM, 0)
-            for v in DEC_VARIANTS:
-                L.bz3_b200_set_variant(st.handle, CM + 200, v)
-                best, ok = 1e9, True
-                for _ in range(args.reps):
-                    got = np.zeros(n + 8, np.uint8)
-                    t0 = time.perf_counter()
-                    rc = L.bz3_b200_stage_cm_decode(st.handle, want.ctypes.data_as(u8p), rw, got.ctypes.data_as(u8p), n)
-                    best = min(best, time.perf_counter() - t0)
-                    ok = ok and rc == 0 and bytes(got[:n]) == bytes(bwt[:n])
-                # truncated stream: same bytes as the oracle produces from it
-                cut = max(rw - 5, 0)
-                dw = np.zeros(n + 8, np.uint8)
-                dg = np.zeros(n + 8, np.uint8)
-                O.orc_cm_decode(want.ctypes.data_as(u8p), cut, dw.ctypes.data_as(u8p), n)
-                L.bz3_b200_stage_cm_decode(st.handle, want.ctypes.data_as(u8p), cut, dg.ctypes.data_as(u8p), n)
-                ok = ok and bytes(dg[:n]) == bytes(dw[:n])
-                rec["dec"][v] = {"ok": bool(ok), "ms": best * 1e3, "MBps": n / best / 1e6,
-                                 "cycles_per_byte_at_1.965GHz": best * 1.965e9 / n}
-                result["ok"] = result["ok"] and ok
-            L.bz3_b200_set_variant(st.handle, CM, 0)
-            result["sets"][name] = rec
-            print(name, "ratio %.3f" % rec["ratio"], flush=True)
-            for v, d in rec["enc"].items():
-                print("  enc v%d  %-5s %8.1f ms  %6.2f MB/s  %6.0f cyc/B   %s" % (v, "OK" if d["ok"] else "FAIL", d["ms"],
-                      d["MBps"], d["cycles_per_byte_at_1.965GHz"], ENC_VARIANTS[v]), flush=True)
-            for v, d in rec["dec"].items():
-                print("  dec v%d  %-5s %8.1f ms  %6.2f MB/s  %6.0f cyc/B   %s" % (v, "OK" if d["ok"] else "FAIL", d["ms"],
-                      d["MBps"], d["cycles_per_byte_at_1.965GHz"], DEC_VARIANTS[v]), flush=True)
+                if kind == "enc":
+                    L.bz3_b200_set_variant(st.handle, CM + 100, v)
+                    for _ in range(args.reps):
+                        got = np.zeros(2 * n + 64, np.uint8)
+                        t0 = time.perf_counter()
+                        rg = L.bz3_b200_stage_cm_encode(st.handle, bwt.ctypes.data_as(u8p), n, got.ctypes.data_as(u8p))
+                        best = min(best, time.perf_counter() - t0)
+                        ok = ok and rg == rw and bytes(got[:rw]) == bytes(want[:rw])
+                else:
+                    L.bz3_b200_set_variant(st.handle, CM + 200, v)
+                    for _ in range(args.reps):
+                        got = np.zeros(n + 8, np.uint8)
+                        t0 = time.perf_counter()
+                        rc = L.bz3_b200_stage_cm_decode(st.handle, want.ctypes.data_as(u8p), rw, got.ctypes.data_as(u8p), n)
+                        best = min(best, time.perf_counter() - t0)
+                        ok = ok and rc == 0 and bytes(got[:n]) == bytes(bwt[:n])
+                    dg = np.zeros(n + 8, np.uint8)   # truncated stream: same bytes as the oracle produces from it
+                    L.bz3_b200_stage_cm_decode(st.handle, want.ctypes.data_as(u8p), cut, dg.ctypes.data_as(u8p), n)
+                    ok = ok and bytes(dg[:n]) == bytes(dw[:n])
+                L.bz3_b200_set_variant(st.handle, CM, 0)
+                d = {"ok": bool(ok), "ms": best * 1e3, "MBps": n / best / 1e6, "cycles_per_byte_at_1.965GHz": best * 1.965e9 / n}
+                result["sets"][name][kind][v] = d
+                result["ok"] = result["ok"] and bool(ok)
+                print("  %s v%d %-10s %-5s %8.1f ms  %6.2f MB/s  %6.0f cyc/B   %s" % (
+                    kind, v, name, "OK" if ok else "FAIL", d["ms"], d["MBps"], d["cycles_per_byte_at_1.965GHz"],
+                    (ENC_VARIANTS if kind == "enc" else DEC_VARIANTS)[v]), flush=True)
+                with open(args.out, "w") as f:
+                    json.dump(result, f, indent=1)
         # whole-block round trip with the new kernels selected through the public block API
         blk = np.ascontiguousarray(sets[0][1][: min(n, 1 << 20)])
         enc_o, r_o, e_o = refs.oracle_encode_block(bytes(blk), max(n, 1 << 20))
