@@ -573,8 +573,11 @@ BZ_D void cm_ptab_put(u32* ptab, int idx, u32 m) {
     else reinterpret_cast<uint2*>(ptab)[idx] = make_uint2(m, 0u - m);
 }
 
-// model thread of the tree decoders: owner of tree node `node` (0 is a dummy)
-template <int LAYOUT>
+// model thread of the tree decoders: owner of tree node `node` (0 is a dummy).
+// PROTO 0: "byte ready" is a plain barrier.  PROTO 1 (walker kernel): it is a barrier-OR that tells whether a
+// walker published the byte; if not, the walkers run up to two more barriers (exact per-path test, serial redo)
+// in which the model threads simply take part.
+template <int LAYOUT, int PROTO = 0>
 BZ_D void cm_dec_model_thread(u16* cm_smem, u32* ptab, volatile u32* vbyte, s32 n, const int node) {
     // ------------------------------------------------------------------ model thread
     // Owns one node; its counters are carried in registers (only this thread writes them).  While the
@@ -633,7 +636,12 @@ BZ_D void cm_dec_model_thread(u16* cm_smem, u32* ptab, volatile u32* vbyte, s32 
             const int sse = (int)lo_s + ((((int)hi_s - (int)lo_s) * (int)(p_s & 4095)) >> 12);
             cm_ptab_put<LAYOUT>(ptab, ((i + 1) & 1) * 256 + node, (u32)(sse * 3 + (int)p_s) << 14);
         }
-        __syncthreads();   // byte ready
+        if (PROTO == 0) {
+            __syncthreads();   // byte ready
+        } else {
+            if (!__syncthreads_or(0))
+                if (!__syncthreads_or(0)) __syncthreads();
+        }
         const u32 byte = vbyte[i & 1];
         const bool on = node != 0 && ((256u | byte) >> sh) == (u32)node;
         const bool one = ((byte >> (sh - 1)) & 1u) != 0;
@@ -1541,6 +1549,176 @@ __global__ void __launch_bounds__(kCmDecP2Threads, 1) cm_decode_paths2_kernel(co
 #endif
 }
 
+// ---- walker warps + model threads (variant 6) -------------------------------------------------------------
+// Measured on B200 (profiles/r01_cm_phase_cycles_1MiB.log): the all-paths walk of variant 5 takes 188 + 47
+// cycles per byte (walk + publish barrier) against 443 + 228 for the serial chain warp of variant 0, but
+// variant 5 pays for the model (predict 161 + learn 234) on the critical path because the same threads do
+// both.  Here the two are separated again: threads 0..255 are walkers (one root-to-leaf path each, as in
+// variant 5), threads 256..511 are the model threads of variant 0/4 (one tree node each, counters in
+// registers, speculating that the byte repeats while the walkers walk).  Per byte:
+//     model    [predict -> B1]  precompute both update outcomes, predict byte i+1 under "byte repeats"  B2  learn
+//     walkers  [B1]  8 loads, 8 dependent IMAD.WIDE, final test, winner publishes               B2  read state
+// B1 is skipped on a speculation hit.  B2 is a barrier-OR: when no walker passed the (sufficient) fast test the
+// candidates apply the reference's exact shift test to their own paths (second barrier-OR) and only if the true
+// path really needs a shift thread 0 redoes the byte with the reference loop (third barrier).
+constexpr int kCmDecW6Threads = 512;
+constexpr size_t kCmDecW6SmemBytes = (size_t)kCmTableU16 * 2 + 2 * 256 * 8 + 2048 + 128 + 256 * 28 * 4;
+
+struct CmWalkConsts {
+    SmemAddr pa[8];   // shared address of this path's {M | -M} word at level k (half 0)
+    u32 cs[9];        // +1 / 0 / -1 (mod 2^32): coefficient of range_k in  low_8 - low_0
+    u32 zk[8];        // all-ones where the path takes the 0-branch (exact test only)
+};
+struct CmWalkState {
+    u32 low, range, code, prevb;
+    s32 ip, wlo;
+    bool have;
+};
+
+template <int HALF>
+BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u32* ptab, u8* scode, volatile u32* pub,
+                           SmemAddr pub_a, const u8* __restrict__ in, const s32 insize, u8* __restrict__ out,
+                           const u32 v) {
+    if (!S.have) __syncthreads();   // B1: ptab ready (skipped when the speculation of the model threads hit)
+    constexpr int HB = HALF * 2048;   // byte offset of this byte's half of ptab
+    constexpr int PB = HALF * 32;     // byte offset of this byte's publication slot
+    u32 rk[9];
+    u32 zmin = 0xFFFFFFFFu;
+    rk[0] = S.range;
+    {
+        const u32 mm[8] = {lds_u32<HB>(K.pa[0]), lds_u32<HB>(K.pa[1]), lds_u32<HB>(K.pa[2]), lds_u32<HB>(K.pa[3]),
+                           lds_u32<HB>(K.pa[4]), lds_u32<HB>(K.pa[5]), lds_u32<HB>(K.pa[6]), lds_u32<HB>(K.pa[7])};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u64 w = cm_mul_wide(rk[k], mm[k]);
+            rk[k + 1] = (u32)(w >> 32);
+            zmin = min(zmin, (u32)w);
+        }
+    }
+    u32 acc = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) acc += K.cs[k] * rk[k];
+    const u32 r8 = rk[8];
+    const u32 d8 = S.code - S.low - acc;
+    const bool cand = d8 <= r8 && zmin != 0u;
+    const bool ok = cand && r8 >= (1u << 24);   // ranges only shrink along a path: r8 is the smallest
+    if (ok) {
+        sts_u32<PB + 0>(pub_a, v);
+        sts_u32<PB + 4>(pub_a, S.code - d8);
+        sts_u32<PB + 8>(pub_a, r8);
+        sts_u32<64 + HALF * 4>(pub_a, v);   // the byte slot the model threads read
+    }
+    if (!__syncthreads_or(ok ? 1 : 0)) {   // B2: byte and state published -- or nobody passed the fast test
+        bool ok2 = false;
+        if (cand) {   // reference's shift test on my own path
+            u32 al = S.low, tmin = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                al += K.zk[k] & (rk[k] - rk[k + 1]);
+                tmin = min(tmin, al ^ (al + rk[k + 1]));
+            }
+            ok2 = tmin >= (1u << 24);
+            if (ok2) {
+                sts_u32<PB + 0>(pub_a, v);
+                sts_u32<PB + 4>(pub_a, S.code - d8);
+                sts_u32<PB + 8>(pub_a, r8);
+                sts_u32<64 + HALF * 4>(pub_a, v);
+            }
+        }
+        if (!__syncthreads_or(ok2 ? 1 : 0)) {
+            if (v == 0) {   // exact serial decoder for this byte (reference loop)
+                u32 flow = S.low, frange = S.range, fcode = S.code;
+                s32 fip = S.ip;
+                const u32 nd = cm_dec_exact_levels(ptab + HALF * 512, 1u, 8, flow, frange, fcode, fip, insize, scode);
+                pub[HALF * 8 + 0] = nd & 255u;
+                pub[HALF * 8 + 1] = flow;
+                pub[HALF * 8 + 2] = frange;
+                pub[HALF * 8 + 3] = fcode;
+                pub[HALF * 8 + 4] = (u32)fip;
+                pub[16 + HALF] = nd & 255u;
+            }
+            __syncthreads();
+            S.code = pub[HALF * 8 + 3];
+            S.ip = (s32)pub[HALF * 8 + 4];
+        }
+    }
+    const u32 byte = lds_u32<PB + 0>(pub_a);
+    S.low = lds_u32<PB + 4>(pub_a);
+    S.range = lds_u32<PB + 8>(pub_a);
+    if (v == 0) out[i] = (u8)byte;
+    if (S.ip - S.wlo >= 1024) {   // uniform; visibility to the serial reader is ordered by the next barrier
+        for (int k = (int)v; k < 1024; k += 256) {
+            const s32 src = S.wlo + 2048 + k;
+            scode[src & 2047] = (src < insize) ? in[src] : 0;
+        }
+        S.wlo += 1024;
+    }
+    S.have = byte == S.prevb;
+    S.prevb = byte;
+}
+
+__global__ void __launch_bounds__(kCmDecW6Threads, 1) cm_decode_walkers_kernel(const u8* __restrict__ in, s32 insize,
+                                                                              u8* __restrict__ out, s32 n) {
+    BZ_DYN_SMEM(u16, cm_smem);
+    u32* ptab = reinterpret_cast<u32*>(cm_smem + kCmTableU16);  // [2][256] {M, -M}; byte i uses half i&1
+    u8* scode = reinterpret_cast<u8*>(ptab + 1024);             // [2048] window of the compressed stream
+    // [0..7], [8..15]: publication slot of even / odd bytes (byte, low, range, code, ip); [16], [17]: the byte
+    // again, where the model threads look for it
+    volatile u32* pub = reinterpret_cast<volatile u32*>(scode + 2048);
+    cm_tables_init_smem(cm_smem);
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 2048; k += kCmDecW6Threads) scode[k] = (k < insize) ? in[k] : 0;
+    if (tid >= 256) {
+        __syncthreads();
+        cm_dec_model_thread<1, 1>(cm_smem, ptab, pub + 16, n, tid - 256);
+        return;
+    }
+    // ---------------------------------------------------------------------- walker: leaf v = tid
+    const u32 v = (u32)tid;
+    CmWalkConsts K;
+    {
+        // level k visits node (1 << k) | (v >> (8 - k)) and takes branch bit 7-k of v
+        u32 zprev = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const u32 b = (v >> (7 - k)) & 1u;
+            const u32 nodek = (1u << k) | (v >> (8 - k));
+            K.pa[k] = smem_addr_of(ptab) + 4 * (nodek * 2 + (b ? 0u : 1u));
+            K.zk[k] = b ? 0u : 0xFFFFFFFFu;
+            const u32 z = b ? 0u : 1u;
+            K.cs[k] = z - zprev;
+            zprev = z;
+        }
+        K.cs[8] = 0u - zprev;
+        volatile u32* scr = pub + 32 + 28 * v;   // private scratch behind the publication slots
+#if !defined(BZ_EMU)
+        launder_u32(K.pa, scr);
+#endif
+        launder_u32(K.cs, scr + 8);
+        launder_u32(K.zk, scr + 17);
+    }
+    __syncthreads();
+    CmWalkState S;
+    S.wlo = 0;
+    S.ip = 0;
+    S.low = 0;
+    S.range = 0xFFFFFFFFu;
+    S.code = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 add = (S.ip < insize) ? (u32)scode[S.ip & 2047] : 0xFFFFFFFFu;  // read_in() past the end adds -1
+        S.ip += (S.ip < insize);
+        S.code = (S.code << 8) + add;
+    }
+    S.have = false;
+    S.prevb = 0;
+    const SmemAddr pub_a = smem_addr_of(pub);
+    for (s32 i = 0; i < n; i += 2) {
+        cm_dec_walk_step<0>(K, S, i, ptab, scode, pub, pub_a, in, insize, out, v);
+        if (i + 1 < n) cm_dec_walk_step<1>(K, S, i + 1, ptab, scode, pub, pub_a, in, insize, out, v);
+    }
+}
+
 #if defined(__CUDACC__)
 inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
@@ -1552,6 +1730,7 @@ inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecLanesSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecP2SmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_walkers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes));
     return cudaSuccess;
 }
 #endif

@@ -61,8 +61,8 @@ def bwt_of(data: np.ndarray) -> np.ndarray:
 def cm_inputs():
     rng = np.random.default_rng(99)
     cases = [(name, arr(d)[:3000]) for name, d in synth.edge_cases() if len(d) > 0]
-    cases.append(("bwt_zipf_48k", bwt_of(synth.zipf_text(48 << 10, seed=7))))
-    cases.append(("bwt_source_32k", bwt_of(synth.source_corpus(32 << 10, seed=8))))
+    cases.append(("bwt_zipf_24k", bwt_of(synth.zipf_text(24 << 10, seed=7))))
+    cases.append(("bwt_source_16k", bwt_of(synth.source_corpus(16 << 10, seed=8))))
     cases.append(("random_6k", rng.integers(0, 256, 6000, dtype=np.uint8)))
     cases.append(("runs_20k", np.repeat(rng.integers(0, 4, 200, dtype=np.uint8), 100)))
     cases.append(("one_byte", np.array([65], np.uint8)))
@@ -73,7 +73,7 @@ CM_CASES = cm_inputs()
 CM_IDS = [c[0] for c in CM_CASES]
 
 ENC_VARIANTS = [0, 1, 2, 4]
-DEC_VARIANTS = [0, 1, 3, 4, 5]
+DEC_VARIANTS = [0, 1, 3, 4, 5, 6]
 
 
 @pytest.mark.parametrize("variant", ENC_VARIANTS)
@@ -97,7 +97,7 @@ def test_cm_decode_kernels(name, data, variant):
     enc = np.zeros(2 * n + 64, np.uint8)
     r = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(enc))
     # the whole stream, a truncated stream (read_in() past the end adds -1) and an empty one
-    for insize in (r, max(r - 3, 0), r // 2, 0):
+    for insize in ((r, max(r - 3, 0), r // 2, 0) if n <= 8000 else (r, max(r - 3, 0))):
         want = np.zeros(n + 8, np.uint8)
         got = np.zeros(n + 8, np.uint8)
         O.orc_cm_decode(refs.ptr(enc), insize, refs.ptr(want), n)
@@ -111,7 +111,7 @@ def test_cm_decode_kernels(name, data, variant):
 def test_cm_kernels_other_schedules(schedule):
     """Same result when the fibers are scheduled in descending or pseudo-random order."""
     E, O = emu(), refs.oracle()
-    data = CM_CASES[CM_IDS.index("bwt_zipf_48k")][1][:12000]
+    data = CM_CASES[CM_IDS.index("bwt_zipf_24k")][1][:8000]
     n = len(data)
     want = np.zeros(2 * n + 64, np.uint8)
     rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))

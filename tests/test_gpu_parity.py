@@ -152,8 +152,9 @@ def test_stage_unbwt_on_garbage_matches_reference_semantics(st, O):
         assert bytes(got[:n]) == bytes(want[:n]), (t, n, k, idx, first_diff(got[:n], want[:n]))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=["two_tier", "single", "exact_tier_only", "all_paths_decode",
-                                                           "one_mul_enc_lanes_dec", "paths2_decode"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6],
+                         ids=["two_tier", "single", "exact_tier_only", "all_paths_decode", "one_mul_enc_lanes_dec",
+                              "paths2_decode", "walkers_decode"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_stage_cm(st, O, name, data, variant):
     a = arr(data)
