@@ -255,7 +255,7 @@ cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, i
 
 // Entropy-stage kernels.  Encoder: 0 chunked pipeline with the select/mul.hi coder lane, 1 single lane
 // (cross-check), 2 chunked with the whole-byte exact tier (cross-check), 4 chunked with the one-multiply
-// coder lane.  Decoder: 0 tree kernel with a serial chain warp, 1 single lane, 3 all-paths (first edition),
+// coder lane (two-tier), 6 chunked with the one-multiply coder lane, single tier, software pipelined.  Decoder: 0 tree kernel with a serial chain warp, 1 single lane, 3 all-paths (first edition),
 // 4 tree kernel with the lane-parallel chain warp, 5 all-paths with one multiply per level, 6 walker warps
 // (the all-paths walk of 5) next to the model threads of 0/4.
 // Defaults can be overridden per process with BZ3_B200_CM_ENC / BZ3_B200_CM_DEC (tuning, tests).
@@ -275,6 +275,8 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
         cm_encode_chunked_kernel<1><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     else if (s->cm_enc == 4)
         cm_encode_chunked_kernel<2><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+    else if (s->cm_enc == 6)
+        cm_encode_chunked_kernel<3><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     else
         cm_encode_chunked_kernel<0><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
     BZ_NOTE_LAUNCH();

@@ -390,6 +390,74 @@ BZ_D void rc_byte2(u32& low, u32& range, s32& op, const u32 sym, const uint4 ca,
 #endif
 }
 
+// MODE 3 coder lane: one multiply per decision, exact shift test per decision, resume after the first event.
+// Measured on B200 (profiles/r01_ubench_b200.log, r01_cm_phase_cycles_1MiB.log): a dependent IMAD.WIDE costs
+// 10 cycles, a taken branch ~20, and redoing a whole byte in the exact tier ~700.  So: the eight decisions
+// of a byte run without any branch -- product of decision k+1 issued from the new range right away, the
+// reference's shift test (low ^ high < 2^24) and the exactness test of the -M shortcut (zero low half) of
+// decision k folded into a bit mask next to it -- and ONE branch per byte asks whether anything happened.
+// If so, the decisions before the first event stand; from that decision on the byte is finished with the
+// reference loop (about once per 4-5 bytes of BWT text, ~4 decisions on average).
+BZ_D void rc_byte3(u32& low, u32& range, u64& w, s32& op, const u32 sym, const uint4 ca, const uint4 cb, const u32 mfirst_next,
+                   const u32* __restrict__ mrow, u8* __restrict__ out) {
+    const u32 m[9] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, mfirst_next};
+    u32 rk[9];   // range before decision k (rk[8]: after the byte)
+    u32 l = low, tmin = 0xFFFFFFFFu, zmin = 0xFFFFFFFFu;
+    u64 ww = w;
+    rk[0] = range;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const u32 rn = (u32)(ww >> 32);
+        zmin = min(zmin, (u32)ww);
+        ww = cm_mul_wide(rn, m[k + 1]);
+        if (!(sym & (0x80u >> k))) l += rk[k] - rn;
+        rk[k + 1] = rn;
+        tmin = min(tmin, l ^ (l + rn));
+    }
+    if (tmin < (1u << 24) || zmin == 0u) {
+        // something happened: find the first decision with an event (cheap: the ranges are known) ...
+        l = low;
+        int kf = 0;
+        for (; kf < 8; kf++) {
+            u32 rb, ra;   // rk[kf], rk[kf + 1] without dynamic register indexing
+            rb = rk[0]; ra = rk[1];
+#pragma unroll
+            for (int j = 1; j < 8; j++) {
+                rb = (j == kf) ? rk[j] : rb;
+                ra = (j == kf) ? rk[j + 1] : ra;
+            }
+            const bool bit = (sym & (0x80u >> kf)) != 0;
+            const u32 ln = bit ? l : l + (rb - ra);
+            const u32 mk = mrow[kf];
+            if (((ln ^ (ln + ra)) < (1u << 24)) || (u32)(rb * mk) == 0u) break;   // lo32 of the product
+            l = ln;
+        }
+        // ... the decisions before it stand; from it on the byte is finished with the reference loop
+        u32 r = rk[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) r = (j == kf) ? rk[j] : r;
+        u32 high = l + r;
+        for (int k = kf; k < 8; k++) {   // src/libbz3.c:388-416
+            const bool bit = (sym & (0x80u >> k)) != 0;
+            const u32 mk = mrow[k];
+            const u32 x = __umulhi(high - l, bit ? mk : 0u - mk);
+            if (bit) high = l + x; else l += x + 1u;
+            while ((l ^ high) < (1u << 24)) {
+                out[op++] = (u8)(l >> 24);
+                l <<= 8;
+                high = (high << 8) | 0xFFu;
+            }
+        }
+        low = l;
+        range = high - l;
+        w = cm_mul_wide(range, mfirst_next);
+        return;
+    }
+    low = l;
+    range = rk[8];
+    w = ww;
+}
+
 // Three-stage chunk pipeline (one __syncthreads per chunk, no polling):
 //   warp 0, lanes 0..7  stage 1: c0 / c1 counters of tree depth `lane`  -> mixed probability p (16 bit)
 //   warp 2, lanes 0..7  stage 2: SSE rows c2 of depth `lane`            -> P << 14
@@ -397,7 +465,7 @@ BZ_D void rc_byte2(u32& low, u32& range, s32& op, const u32 sym, const uint4 ca,
 // Stage s works on chunk it-s in iteration `it`.  A node of depth d is only ever coded at bit position d,
 // so the eight lanes of a stage own disjoint counters and never synchronise with each other.
 template <int MODE>
-__global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const u8* __restrict__ in, s32 n,
+__global__ void __launch_bounds__(kCmEncThreads, 1) cm_encode_chunked_kernel(const u8* __restrict__ in, s32 n,
                                                                          u8* __restrict__ out, s32* out_size) {
     BZ_DYN_SMEM(u16, cm_smem);
     u32* pbuf = reinterpret_cast<u32*>(cm_smem + kCmTableU16);                 // [2][chunk * 8]  P << 14
@@ -469,7 +537,7 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                     {
                         const u32 m = (u32)(sse * 3 + p) << 14;
                         // MODE 2: the coder lane multiplies by M for a 1-bit and by -M for a 0-bit (see rc_fast_byte2)
-                        pb[k * 8] = (MODE == 2 && !ones) ? 0u - m : m;
+                        pb[k * 8] = (MODE >= 2 && !ones) ? 0u - m : m;
                     }
                     cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
                     cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
@@ -488,6 +556,7 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                 uint4 a = pv[0], b = pv[1];
                 u32 sym = sb[0];
                 u32 x = mulhi_pinned(range, a.x);
+                u64 w3 = (MODE == 3) ? cm_mul_wide(range, a.x) : 0ull;   // MODE 3: product of the first decision
                 for (s32 k = 0; k < len; k++) {
                     const uint4 ca = a, cb = b;
                     const u32 cs = sym;
@@ -505,7 +574,9 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_chunked_kernel(const 
                         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym) : "r"(sp));
 #endif
                     }
-                    if (MODE == 2) {
+                    if (MODE == 3) {
+                        rc_byte3(low, range, w3, op, cs, ca, cb, a.x, pw + 8 * k, out);
+                    } else if (MODE == 2) {
 #ifdef BZ_CM_PROFILE
                         rc_byte2(low, range, op, cs, ca, cb, out, _ex);
 #else
@@ -1726,6 +1797,7 @@ inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_chunked_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmEncSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecLanesSmemBytes));

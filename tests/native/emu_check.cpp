@@ -34,6 +34,10 @@ EXPORT int32_t emu_cm_encode(int variant, const uint8_t* in, int32_t n, uint8_t*
             b.x = kCmEncThreads;
             emu::launch(g, b, kCmEncSmemBytes, [&] { cm_encode_chunked_kernel<2>(in, n, out, &res); });
             break;
+        case 6:
+            b.x = kCmEncThreads;
+            emu::launch(g, b, kCmEncSmemBytes, [&] { cm_encode_chunked_kernel<3>(in, n, out, &res); });
+            break;
         default:
             return -777;
     }

@@ -154,7 +154,7 @@ def test_stage_unbwt_on_garbage_matches_reference_semantics(st, O):
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6],
                          ids=["two_tier", "single", "exact_tier_only", "all_paths_decode", "one_mul_enc_lanes_dec",
-                              "paths2_decode", "walkers_decode"])
+                              "paths2_decode", "resume_enc_walkers_dec"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_stage_cm(st, O, name, data, variant):
     a = arr(data)

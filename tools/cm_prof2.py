@@ -38,7 +38,7 @@ def main():
             L.bz3_b200_stage_bwt(st.handle, data.ctypes.data_as(u8p), n, bwt.ctypes.data_as(u8p))
             enc = np.zeros(2 * n + 64, np.uint8)
             rec = {}
-            for v in (0, 4):
+            for v in (0, 4, 6):
                 L.bz3_b200_set_variant(st.handle, CM + 100, v)
                 r = L.bz3_b200_stage_cm_encode(st.handle, bwt.ctypes.data_as(u8p), n, enc.ctypes.data_as(u8p))
                 p = prof()

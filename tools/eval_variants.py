@@ -23,7 +23,8 @@ from bzip3_b200 import synth  # noqa: E402
 from tests import refs  # noqa: E402
 
 CM = 5  # BZ3_STAGE_CM
-ENC_VARIANTS = {0: "chunked, select+mul.hi coder lane (round-1 default)", 4: "chunked, one-multiply coder lane"}
+ENC_VARIANTS = {0: "chunked, select+mul.hi coder lane (round-1 default)", 4: "chunked, one-multiply coder lane, two-tier",
+                6: "chunked, one-multiply coder lane, branch-free byte + resume at first event"}
 DEC_VARIANTS = {0: "tree, serial chain warp (round-1 default)", 3: "all paths, first edition",
                 4: "tree, lane-parallel chain warp", 5: "all paths, one multiply per level",
                 6: "walker warps (all-paths walk) + model threads"}
@@ -67,7 +68,7 @@ def main():
             print("%s: ratio %.3f, oracle on one host core: enc %.1f MB/s, dec %.1f MB/s" % (
                 name, rw / n, n / cpu_enc / 1e6, n / cpu_dec / 1e6), flush=True)
         # known-good kernels first, so that a fault in a new one cannot hide the baseline
-        order = [("enc", 0), ("dec", 0), ("enc", 4), ("dec", 5), ("dec", 4), ("dec", 6)]
+        order = [("enc", 0), ("dec", 0), ("enc", 4), ("dec", 4), ("enc", 6), ("dec", 6), ("dec", 5)]
         for kind, v in order:
             for name, _ in sets:
                 bwt, want, rw, cut, dw = prep[name]
@@ -104,7 +105,7 @@ def main():
         blk = np.ascontiguousarray(sets[0][1][: min(n, 1 << 20)])
         enc_o, r_o, e_o = refs.oracle_encode_block(bytes(blk), max(n, 1 << 20))
         combos = {}
-        for ve, vd in ((4, 4), (4, 5), (4, 6)):
+        for ve, vd in ((4, 4), (6, 6), (6, 5)):
             L.bz3_b200_set_variant(st.handle, CM + 100, ve)
             L.bz3_b200_set_variant(st.handle, CM + 200, vd)
             buf = np.zeros(refs.bound(max(n, 1 << 20)) + 64, np.uint8)
