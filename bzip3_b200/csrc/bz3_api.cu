@@ -187,6 +187,8 @@ cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* 
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
     if (s->variant[BZ3_STAGE_LZP] == 1)
         lzp_encode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    else if (s->variant[BZ3_STAGE_LZP] == 2)   // several windows in flight (opt-in until timed on the GPU)
+        lzp_encode_warp_pf_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else
         lzp_encode_warp_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
@@ -202,6 +204,8 @@ cudaError_t run_lzp_decode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32 m
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
     if (s->variant[BZ3_STAGE_LZP] == 1)
         lzp_decode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    else if (s->variant[BZ3_STAGE_LZP] == 2)   // bulk decoder (opt-in until timed on the GPU)
+        lzp_decode_bulk_kernel<<<1, kLzpBulkThreads, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else
         lzp_decode_warp_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();

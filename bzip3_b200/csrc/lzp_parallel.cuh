@@ -136,6 +136,199 @@ __global__ void __launch_bounds__(32) lzp_encode_warp_kernel(const u8* __restric
     if (lane == 0) *result = op >= out_stop ? -1 : op;
 }
 
+// ---- encoder with several windows in flight (variant 2) -----------------------------------------------------
+// Measured on B200: the windowed encoder above takes ~1700 cycles per window of 32 positions, which is two
+// dependent L2 round trips (table probe, then the quick-check words at the probed position) and little else.
+// This version reads the table and the quick-check words for kLzpPf consecutive windows at once and then
+// commits the windows in order exactly as before.  What the sequential algorithm would have read can differ from
+// the early read only if an earlier window OF THE SAME GROUP wrote that table slot; a bitmap of the 2^18 slots
+// in shared memory (32 KiB) records the slots written by the group, and a lane whose slot is marked (or whose
+// predecessor is a lower lane of its own window) simply reads again at commit time.  A match ends the group
+// (the positions behind it shift).  The tail of the block and everything near scan_end run on the one-window
+// path, which is the kernel above verbatim.
+constexpr int kLzpPf = 8;
+
+struct LzpEncState {
+    s32 ip, op, veto_until;
+};
+
+// Commits one window.  `ref`, `ra`, `rb` are what the lane read early (table entry and the words at ref+36 / ref),
+// `pa`, `pb` the words of its own position; `fresh` tells whether the early read is still what the sequential
+// algorithm would see (slot not written since).  Returns true when a match was taken.
+BZ_D bool lzp_encode_commit_window(const u8* __restrict__ in, u8* __restrict__ out, s32* __restrict__ lut, u32* dirty,
+                                   const s32 W, const bool phase0, const s32 scan_end, const s32 out_stop, const u32 lane,
+                                   const u32 lt, const u32 h, s32 ref, const u32 pa, const u32 pb, u32 ra, u32 rb,
+                                   bool fresh, LzpEncState& S, bool& stored) {
+    const s32 ip = S.ip;
+    const bool active = (s32)lane < W;
+    const s32 p = ip + (s32)lane;
+    const u8 b = (u8)(pb & 0xFFu);
+    const u32 peers = __match_any_sync(kFullMask, h);
+    const u32 lower = peers & lt;
+    if (active && dirty && !lower) fresh = fresh && !((dirty[h >> 5] >> (h & 31u)) & 1u);
+    const bool redo = active && (lower != 0u || !fresh);
+    if (__any_sync(kFullMask, redo)) {
+        if (redo) {
+            // the nearest lower lane with the same hash wrote the slot last; otherwise read the table again
+            ref = lower ? ip + (31 - __clz((int)lower)) : __ldcg(&lut[h]);
+            if (phase0 && ref > 0) {
+                ra = lzp_ld32(in + ref + kLzpMinMatch - 4);
+                rb = lzp_ld32(in + ref);
+            }
+        }
+    }
+    s32 match_lane = -1, mlen = 0;
+    if (phase0) {
+        const bool qc = active && ref > 0 && pa == ra && pb == rb;
+        u32 cand = __ballot_sync(kFullMask, qc);
+        while (cand) {
+            const int l = __ffs((int)cand) - 1;
+            cand &= cand - 1;
+            const s32 pl = ip + l;
+            const s32 rl = __shfl_sync(kFullMask, ref, l);
+            if (S.veto_until > pl && lzp_ld32(in + S.veto_until) != lzp_ld32(in + rl + (S.veto_until - pl))) continue;
+            s32 len = lzp_warp_match_words(in, pl, rl, scan_end, lane);
+            if (len < kLzpMinMatch) {
+                if (S.veto_until < pl + len) S.veto_until = pl + len;
+                continue;
+            }
+            len += in[pl + len] == in[rl + len];
+            len += in[pl + len] == in[rl + len];
+            len += in[pl + len] == in[rl + len];
+            match_lane = l;
+            mlen = len;
+            break;
+        }
+    }
+    // positions ip .. ip+nvis-1 are visited (the match start included): they own their table slot
+    const s32 nvis = match_lane >= 0 ? match_lane + 1 : W;
+    const bool visited = (s32)lane < nvis;
+    const u32 vis_peers = peers & __ballot_sync(kFullMask, visited);
+    stored = visited && (31 - __clz((int)vis_peers)) == (int)lane;   // last visited lane of a hash wins
+    if (stored) {
+        __stcg(&lut[h], p);
+        if (dirty) atomicOr(&dirty[h >> 5], 1u << (h & 31u));
+    }
+    // literals: lanes below the match (or the whole window); an escape byte with a live slot takes two bytes
+    const s32 nlit = match_lane >= 0 ? match_lane : W;
+    const bool lit = (s32)lane < nlit;
+    const bool esc = lit && b == kLzpEscape && ref > 0;
+    const u32 escm = __ballot_sync(kFullMask, esc);
+    if (lit) {
+        u8* o = out + S.op + lane + __popc(escm & lt);
+        o[0] = b;
+        if (esc) o[1] = 255;
+    }
+    S.op += nlit + __popc(escm);
+    if (match_lane >= 0) {
+        s32 o = S.op;
+        if (lane == 0) {
+            out[o++] = (u8)kLzpEscape;
+            s32 code = mlen - kLzpMinMatch;
+            while (code >= 254) {
+                code -= 254;
+                out[o++] = 254;
+                if (o >= out_stop) break;
+            }
+            out[o++] = (u8)code;
+        }
+        S.op = __shfl_sync(kFullMask, o, 0);
+        S.ip += match_lane + mlen;
+    } else {
+        S.ip += W;
+    }
+    __syncwarp();
+    return match_lane >= 0;
+}
+
+__global__ void __launch_bounds__(32) lzp_encode_warp_pf_kernel(const u8* __restrict__ in, s32 n, u8* __restrict__ out,
+                                                                s32* __restrict__ lut, s32* __restrict__ result) {
+    __shared__ u32 dirty[kLzpSlots / 32];
+    const u32 lane = lane_id();
+    const u32 lt = lanemask_lt();
+    if (n < kLzpMinMatch + 32) {
+        if (lane == 0) *result = -1;
+        return;
+    }
+    for (int k = lane; k < kLzpSlots / 32; k += 32) dirty[k] = 0;
+    __syncwarp();
+    const s32 out_stop = n - 8;
+    const s32 scan_end = n - kLzpMinMatch - 32;
+    if (lane < 4) out[lane] = in[lane];
+    LzpEncState S;
+    S.ip = 4;
+    S.op = 4;
+    S.veto_until = 0;
+    // groups of kLzpPf full windows
+    while (S.ip + 32 * kLzpPf <= scan_end && S.op < out_stop) {
+        u32 h[kLzpPf], pa[kLzpPf], pb[kLzpPf], ra[kLzpPf], rb[kLzpPf];
+        s32 ref[kLzpPf];
+#pragma unroll
+        for (int k = 0; k < kLzpPf; k++) {
+            const s32 p = S.ip + 32 * k + (s32)lane;
+            h[k] = lzp_hash(lzp_context(in, p));
+            ref[k] = __ldcg(&lut[h[k]]);
+            pb[k] = lzp_ld32(in + p);
+            pa[k] = lzp_ld32(in + p + kLzpMinMatch - 4);
+        }
+#pragma unroll
+        for (int k = 0; k < kLzpPf; k++) {
+            ra[k] = 0;
+            rb[k] = 0;
+            if (ref[k] > 0) {
+                ra[k] = lzp_ld32(in + ref[k] + kLzpMinMatch - 4);
+                rb[k] = lzp_ld32(in + ref[k]);
+            }
+        }
+        u32 mine = 0;   // bit k: this lane marked its slot of window k
+        bool stop = false;
+#pragma unroll
+        for (int k = 0; k < kLzpPf; k++) {
+            if (!stop) {
+                bool stored;
+                const bool matched = lzp_encode_commit_window(in, out, lut, dirty, 32, true, scan_end, out_stop, lane, lt, h[k],
+                                                              ref[k], pa[k], pb[k], ra[k], rb[k], true, S, stored);
+                if (stored) mine |= 1u << k;
+                stop = matched || S.op >= out_stop;   // uniform
+            }
+        }
+        // unmark the slots of this group
+#pragma unroll
+        for (int k = 0; k < kLzpPf; k++)
+            if ((mine >> k) & 1u) atomicAnd(&dirty[h[k] >> 5], ~(1u << (h[k] & 31u)));
+        __syncwarp();
+    }
+    // the rest: one window at a time (phase 0: positions that may start a match; phase 1: literal-only tail)
+    for (int phase = 0; phase < 2; phase++) {
+        const s32 limit = phase == 0 ? scan_end : n;
+        while (S.ip < limit && S.op < out_stop) {
+            const s32 W = (limit - S.ip) < 32 ? (limit - S.ip) : 32;
+            const bool active = (s32)lane < W;
+            const s32 p = S.ip + (s32)lane;
+            u32 hh = 0xFFFFFFFFu - lane;  // inactive lanes never collide
+            s32 rf = 0;
+            u32 wa = 0, wb = 0, xa = 0, xb = 0;
+            if (active) {
+                hh = lzp_hash(lzp_context(in, p));
+                rf = __ldcg(&lut[hh]);
+                wb = in[p];
+                if (phase == 0) {
+                    wb = lzp_ld32(in + p);
+                    wa = lzp_ld32(in + p + kLzpMinMatch - 4);
+                    if (rf > 0) {
+                        xa = lzp_ld32(in + rf + kLzpMinMatch - 4);
+                        xb = lzp_ld32(in + rf);
+                    }
+                }
+            }
+            bool stored;
+            lzp_encode_commit_window(in, out, lut, nullptr, W, phase == 0, scan_end, out_stop, lane, lt, hh, rf, wa, wb, xa, xb,
+                                     true, S, stored);
+        }
+    }
+    if (lane == 0) *result = S.op >= out_stop ? -1 : S.op;
+}
+
 __global__ void __launch_bounds__(32) lzp_decode_warp_kernel(const u8* __restrict__ in, s32 n, u8* __restrict__ out,
                                                              s32 max, s32* __restrict__ lut, s32* __restrict__ result) {
     const u32 lane = lane_id();
@@ -237,6 +430,173 @@ __global__ void __launch_bounds__(32) lzp_decode_warp_kernel(const u8* __restric
         }
     }
     if (lane == 0) *result = status < 0 ? -1 : op;
+}
+
+// ---- bulk decoder (variant 2) --------------------------------------------------------------------------------
+// The sequential decoder reads the table only when the input byte is 0xF2; everything between two such bytes
+// is a run of literals whose only side effect is  table[hash(context)] = position  for every position -- and
+// positions only grow, so those updates are an order-free scatter-max.  One CTA therefore alternates
+//   A  find the first 0xF2 in the next (up to) 8 KiB of input: 16 bytes per thread, block-wide min
+//   B  copy the literals before it and scatter-max their positions into the table, all threads at once
+//   C  one thread resolves the 0xF2 against the (now complete) table exactly like the reference -- plain
+//      literal when the slot is empty, escaped literal, or a match, which all threads copy (periodic when it
+//      overlaps itself).
+// Text with few matches decodes at copy speed instead of one L2/atomic round per 32 bytes; a match costs a few
+// barriers and one table round trip.
+constexpr int kLzpBulkThreads = 512;
+constexpr int kLzpBulkChunk = kLzpBulkThreads * 16;
+
+__global__ void __launch_bounds__(kLzpBulkThreads) lzp_decode_bulk_kernel(const u8* __restrict__ in, s32 n, u8* __restrict__ out,
+                                                                          s32 max, s32* __restrict__ lut,
+                                                                          s32* __restrict__ result) {
+    __shared__ u32 s_last4[kLzpBulkThreads];   // last four bytes of every thread's slice (little end = oldest)
+    __shared__ s32 s_first[kLzpBulkThreads / 32];
+    __shared__ s32 s_ctl[8];                   // [0] first, [1] kind, [2] count, [3] ref, [4] new ip, [5] status
+    __shared__ u32 s_tail;
+    const int t = threadIdx.x;
+    const u32 lane = lane_id();
+    if (n < 4) {
+        if (t == 0) *result = -1;
+        return;
+    }
+    if (t < 4) out[t] = in[t];
+    s32 ip = 4, op = 4;
+    // the four most recent output bytes, most recent in the low byte (uniform across the CTA)
+    u32 tail = (u32)in[3] | ((u32)in[2] << 8) | ((u32)in[1] << 16) | ((u32)in[0] << 24);
+    s32 status = 0;
+    while (ip < n && op < max) {
+        s32 lim = n - ip;
+        if (max - op < lim) lim = max - op;
+        if (lim > kLzpBulkChunk) lim = kLzpBulkChunk;
+        // ---- A: my 16 bytes, first escape among them
+        const s32 j0 = 16 * t;
+        u8 by[16];
+        s32 mine = kLzpBulkChunk;
+#pragma unroll
+        for (int j = 15; j >= 0; j--) {
+            by[j] = (j0 + j < lim) ? in[ip + j0 + j] : (u8)0;
+            if (j0 + j < lim && by[j] == kLzpEscape) mine = j0 + j;
+        }
+        s_last4[t] = (u32)by[12] | ((u32)by[13] << 8) | ((u32)by[14] << 16) | ((u32)by[15] << 24);
+        s32 m = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const s32 x = __shfl_xor_sync(kFullMask, m, o);
+            m = x < m ? x : m;
+        }
+        if (lane == 0) s_first[t >> 5] = m;
+        __syncthreads();
+        if (t < 32) {
+            s32 v = (t < kLzpBulkThreads / 32) ? s_first[t] : kLzpBulkChunk;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const s32 x = __shfl_xor_sync(kFullMask, v, o);
+                v = x < v ? x : v;
+            }
+            if (t == 0) s_ctl[0] = v;
+        }
+        __syncthreads();
+        const s32 first = s_ctl[0];
+        const s32 nlit = first < lim ? first : lim;
+        // ---- B: literals before the escape: copy + scatter-max of their positions
+        {
+            // context of my byte j = the four bytes before it: previous slice's last four, or the carried tail
+            u32 prev;   // byte k of `prev` is the byte 4-k positions before my slice start... (oldest in the low byte)
+            if (t == 0) prev = ((tail >> 24) & 0xFFu) | (((tail >> 16) & 0xFFu) << 8) | (((tail >> 8) & 0xFFu) << 16) | ((tail & 0xFFu) << 24);
+            else prev = s_last4[t - 1];
+            // sliding window: w holds the four bytes before the current byte, most recent in the low byte
+            u32 w = ((prev & 0xFFu) << 24) | (((prev >> 8) & 0xFFu) << 16) | (((prev >> 16) & 0xFFu) << 8) | ((prev >> 24) & 0xFFu);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j0 + j < nlit) {
+                    out[op + j0 + j] = by[j];
+                    atomicMax(&lut[lzp_hash(w)], op + j0 + j);   // visited positions only grow
+                }
+                w = (w << 8) | (u32)by[j];
+            }
+            // new tail after nlit literals: owned by the thread holding byte nlit-1
+            if (nlit > 0 && (nlit - 1) / 16 == t) {
+                u32 nt = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const s32 idx = nlit - 1 - k;   // chunk index of the k-th most recent byte
+                    u32 b;
+                    if (idx >= j0) {
+                        b = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) b = (j0 + j == idx) ? (u32)by[j] : b;
+                    } else if (idx >= 0) {
+                        b = (prev >> (8 * (idx - (j0 - 4)))) & 0xFFu;   // one of the four bytes before my slice
+                    } else {
+                        b = (tail >> (8 * (-idx - 1))) & 0xFFu;         // still the old tail
+                    }
+                    nt |= b << (8 * k);
+                }
+                s_tail = nt;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (nlit > 0) tail = s_tail;
+        op += nlit;
+        ip += nlit;
+        if (!(first < lim)) continue;   // no escape in this chunk (uniform)
+        // ---- C: the byte at `ip` is 0xF2 (uniform: ip < n and op < max hold because first < lim)
+        if (t == 0) {
+            s32 kind = 0, count = 0, nip = ip;   // kind 0: literal 0xF2, 1: match, -1: truncated
+            const s32 ref = atomicMax(&lut[lzp_hash(tail)], op);
+            if (ref <= 0) {   // empty slot: 0xF2 is an ordinary literal (src/libbz3.c:212, :236)
+                nip = ip + 1;
+            } else {
+                nip = ip + 1;
+                if (nip == n) {
+                    kind = -1;
+                } else if (in[nip] == 255) {   // escaped literal
+                    nip++;
+                } else {
+                    u32 ulen = kLzpMinMatch;  // wraps like the reference's signed 32-bit accumulator
+                    bool truncated = false;
+                    for (;;) {
+                        if (nip == n) { truncated = true; break; }
+                        const u32 c = in[nip++];
+                        ulen += c;
+                        if (c != 254) break;
+                    }
+                    if (truncated) {
+                        kind = -1;
+                    } else {
+                        s64 stop64 = (s64)op + (s64)(s32)ulen;
+                        if (stop64 > max) stop64 = max;
+                        count = stop64 > op ? (s32)(stop64 - op) : 0;
+                        kind = 1;
+                    }
+                }
+            }
+            if (kind == 0) out[op] = (u8)kLzpEscape;
+            s_ctl[1] = kind;
+            s_ctl[2] = count;
+            s_ctl[3] = ref;
+            s_ctl[4] = nip;
+        }
+        __syncthreads();
+        const s32 kind = s_ctl[1], count = s_ctl[2], ref = s_ctl[3];
+        ip = s_ctl[4];
+        if (kind < 0) { status = -1; break; }
+        if (kind == 0) {
+            tail = (tail << 8) | (u32)kLzpEscape;
+            op++;
+        } else if (count > 0) {
+            const s32 dist = op - ref;  // > 0; the source [ref, op) is final, the copy repeats it with period dist
+            for (s32 k = t; k < count; k += kLzpBulkThreads) out[op + k] = __ldcg(out + ref + (dist >= count ? k : k % dist));
+            __threadfence();
+            __syncthreads();
+            op += count;
+            tail = (u32)__ldcg(out + op - 1) | ((u32)__ldcg(out + op - 2) << 8) | ((u32)__ldcg(out + op - 3) << 16) |
+                   ((u32)__ldcg(out + op - 4) << 24);
+        }
+        __syncthreads();   // s_ctl / s_tail are reused by the next round
+    }
+    if (t == 0) *result = status < 0 ? -1 : op;
 }
 
 }  // namespace bz3

@@ -39,6 +39,10 @@ def emu():
         L.emu_cm_decode.argtypes = [C.c_int, refs.u8p, C.c_int32, refs.u8p, C.c_int32]
         L.emu_lzp_encode.restype = C.c_int32
         L.emu_lzp_encode.argtypes = [refs.u8p, C.c_int32, refs.u8p, refs.i32p]
+        L.emu_lzp_encode_pf.restype = C.c_int32
+        L.emu_lzp_encode_pf.argtypes = [refs.u8p, C.c_int32, refs.u8p, refs.i32p]
+        L.emu_lzp_decode_bulk.restype = C.c_int32
+        L.emu_lzp_decode_bulk.argtypes = [refs.u8p, C.c_int32, refs.u8p, C.c_int32, refs.i32p]
         L.emu_lzp_decode.restype = C.c_int32
         L.emu_lzp_decode.argtypes = [refs.u8p, C.c_int32, refs.u8p, C.c_int32, refs.i32p]
         _lib = L
@@ -129,8 +133,18 @@ def test_cm_kernels_other_schedules(schedule):
         E.emu_set_schedule(0, 1)
 
 
+def _lzp_extra():
+    rng = np.random.default_rng(5)
+    rep = np.tile(rng.integers(0, 256, 700, dtype=np.uint8), 60)          # long matches, period 700
+    runs = np.repeat(rng.integers(0, 3, 300, dtype=np.uint8), 150)        # every context repeats inside a window
+    esc = rng.choice(np.array([0xF2, 0x41, 0x42], np.uint8), 30000)       # escape bytes with live slots
+    mix = np.concatenate([rep[:9000], rng.integers(0, 256, 5000, dtype=np.uint8), rep[:9000], runs[:6000], esc[:4000]])
+    return [("periodic_42k", rep), ("runs_45k", runs), ("escapes_30k", esc), ("mix_33k", mix)]
+
+
 LZP_CASES = [(name, arr(d)) for name, d in synth.edge_cases()] + [
-    ("source_96k", synth.source_corpus(96 << 10, seed=21)), ("log_64k", synth.log_stream(64 << 10, seed=22))]
+    ("source_96k", synth.source_corpus(96 << 10, seed=21)), ("log_64k", synth.log_stream(64 << 10, seed=22)),
+    ("zipf_64k", synth.zipf_text(64 << 10, seed=23))] + _lzp_extra()
 
 
 @pytest.mark.parametrize("name,data", LZP_CASES, ids=[c[0] for c in LZP_CASES])
@@ -146,8 +160,14 @@ def test_lzp_warp_kernels(name, data):
     rw = O.orc_lzp_encode(refs.ptr(pad), n, refs.ptr(want), lp)
     rg = E.emu_lzp_encode(refs.ptr(pad), n, refs.ptr(got), lp)
     assert rg == rw
+    got2 = np.zeros(n + 64, np.uint8)
+    lut_after = lut.copy()
+    rg2 = E.emu_lzp_encode_pf(refs.ptr(pad), n, refs.ptr(got2), lp)   # several windows in flight
+    assert rg2 == rw
     if rw > 0:
         assert bytes(got[:rg]) == bytes(want[:rw])
+        assert bytes(got2[:rg2]) == bytes(want[:rw])
+        assert np.array_equal(lut, lut_after)   # same final table as the one-window kernel
         for cut in (rw, rw - 1, rw // 2, 4, 3):
             cap = refs.bound(n)
             dw = np.zeros(cap + 64, np.uint8)
@@ -157,3 +177,21 @@ def test_lzp_warp_kernels(name, data):
             assert sg == sw, (cut, sg, sw)
             if sw > 0:
                 assert bytes(dg[:sg]) == bytes(dw[:sw])
+            lut_w = lut.copy()
+            db = np.zeros(cap + 64, np.uint8)
+            sb = E.emu_lzp_decode_bulk(refs.ptr(want), cut, refs.ptr(db), cap, lp)   # bulk decoder
+            assert sb == sw, (cut, sb, sw)
+            if sw > 0:
+                assert bytes(db[:sb]) == bytes(dw[:sw])
+                assert np.array_equal(lut, lut_w)
+        # output capacity smaller than the decoded size: the copy is clamped like the reference's
+        for cap in (n // 2, 5):
+            if cap < 4:
+                continue
+            dw = np.zeros(n + 64, np.uint8)
+            db = np.zeros(n + 64, np.uint8)
+            sw = O.orc_lzp_decode(refs.ptr(want), rw, refs.ptr(dw), cap, lp)
+            sb = E.emu_lzp_decode_bulk(refs.ptr(want), rw, refs.ptr(db), cap, lp)
+            assert sb == sw, (cap, sb, sw)
+            if sw > 0:
+                assert bytes(db[:sb]) == bytes(dw[:sw])

@@ -81,7 +81,7 @@ def test_stage_rle(st, O, name, data):
         assert bytes(dg[:n]) == bytes(dw[:n]), (cut, first_diff(dg[:n], dw[:n]))
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["warp", "single"])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["warp", "single", "warp_windows_in_flight"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_stage_lzp(st, O, name, data, variant):
     st.L.bz3_b200_set_variant(st.handle, 3, variant)
