@@ -195,3 +195,63 @@ def test_lzp_warp_kernels(name, data):
             assert sb == sw, (cap, sb, sw)
             if sw > 0:
                 assert bytes(db[:sb]) == bytes(dw[:sw])
+
+
+def test_fuzz_all_variants_small_inputs():
+    """Random small inputs (several byte distributions) through every CM and LZP kernel variant."""
+    E, O = emu(), refs.oracle()
+    rng = np.random.default_rng(20260923)
+    lut = np.zeros(1 << 18, np.int32)
+    lp = lut.ctypes.data_as(refs.i32p)
+    for it in range(40):
+        n = int(rng.integers(1, 700))
+        kind = it % 4
+        if kind == 0:
+            data = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == 1:
+            data = rng.choice(np.array([0, 1, 255, 0xF2], np.uint8), n, p=[0.7, 0.1, 0.1, 0.1])
+        elif kind == 2:
+            data = np.repeat(rng.integers(0, 256, n // 7 + 1, dtype=np.uint8), 7)[:n]
+        else:
+            base = rng.integers(0, 256, max(n // 5, 1), dtype=np.uint8)
+            data = np.tile(base, 6)[:n]
+        data = np.ascontiguousarray(data)
+        n = len(data)
+        want = np.zeros(2 * n + 64, np.uint8)
+        rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
+        for v in ENC_VARIANTS:
+            got = np.zeros(2 * n + 64, np.uint8)
+            assert E.emu_cm_encode(v, refs.ptr(data), n, refs.ptr(got)) == rw, (it, v)
+            assert bytes(got[:rw]) == bytes(want[:rw]), (it, v)
+        cut = int(rng.integers(0, rw + 1))
+        dw = np.zeros(n + 8, np.uint8)
+        O.orc_cm_decode(refs.ptr(want), cut, refs.ptr(dw), n)
+        for v in DEC_VARIANTS:
+            back = np.zeros(n + 8, np.uint8)
+            E.emu_cm_decode(v, refs.ptr(want), rw, refs.ptr(back), n)
+            assert bytes(back[:n]) == bytes(data), (it, v)
+            back = np.zeros(n + 8, np.uint8)
+            E.emu_cm_decode(v, refs.ptr(want), cut, refs.ptr(back), n)
+            assert bytes(back[:n]) == bytes(dw[:n]), (it, v, cut)
+        # LZP on a longer, matchy input built from the same bytes
+        long = np.ascontiguousarray(np.tile(data, 1 + 1200 // n)[:1200 + n])
+        m = len(long)
+        pad = np.zeros(m + 64, np.uint8)
+        pad[:m] = long
+        lw = np.zeros(m + 64, np.uint8)
+        r0 = O.orc_lzp_encode(refs.ptr(pad), m, refs.ptr(lw), lp)
+        for fn in (E.emu_lzp_encode, E.emu_lzp_encode_pf):
+            lg = np.zeros(m + 64, np.uint8)
+            assert fn(refs.ptr(pad), m, refs.ptr(lg), lp) == r0, it
+            if r0 > 0:
+                assert bytes(lg[:r0]) == bytes(lw[:r0]), it
+        if r0 > 0:
+            cap = refs.bound(m)
+            for cutl in (r0, int(rng.integers(0, r0 + 1))):
+                d0 = np.zeros(cap + 64, np.uint8)
+                s0 = O.orc_lzp_decode(refs.ptr(lw), cutl, refs.ptr(d0), cap, lp)
+                for fn in (E.emu_lzp_decode, E.emu_lzp_decode_bulk):
+                    d1 = np.zeros(cap + 64, np.uint8)
+                    assert fn(refs.ptr(lw), cutl, refs.ptr(d1), cap, lp) == s0, (it, cutl)
+                    if s0 > 0:
+                        assert bytes(d1[:s0]) == bytes(d0[:s0]), (it, cutl)

@@ -101,6 +101,45 @@ def main():
                     (ENC_VARIANTS if kind == "enc" else DEC_VARIANTS)[v]), flush=True)
                 with open(args.out, "w") as f:
                     json.dump(result, f, indent=1)
+        # LZP pre-pass: one-window kernels (default) against variant 2 (windows in flight / bulk decoder)
+        LZP = 3  # BZ3_STAGE_LZP
+        lzp_sets = sets + [("log", synth.log_stream(n, seed=4245))]
+        result["lzp"] = {}
+        for name, data in lzp_sets:
+            data = np.ascontiguousarray(data[:n])
+            pad = np.zeros(n + 64, np.uint8)
+            pad[:n] = data
+            lut = np.zeros(1 << 18, np.int32)
+            lp = lut.ctypes.data_as(refs.i32p)
+            want = np.zeros(n + 64, np.uint8)
+            rw = O.orc_lzp_encode(pad.ctypes.data_as(u8p), n, want.ctypes.data_as(u8p), lp)
+            rec = {"lzp_size": int(rw)}
+            for v in (0, 2):
+                L.bz3_b200_set_variant(st.handle, LZP, v)
+                got = np.zeros(n + 64, np.uint8)
+                t0 = time.perf_counter()
+                rg = L.bz3_b200_stage_lzp_encode(st.handle, pad.ctypes.data_as(u8p), n, got.ctypes.data_as(u8p))
+                te = time.perf_counter() - t0
+                ok = rg == rw and (rw <= 0 or bytes(got[:rw]) == bytes(want[:rw]))
+                td, okd = 0.0, True
+                if rw > 0:
+                    cap = refs.bound(n)
+                    back = np.zeros(cap + 64, np.uint8)
+                    t0 = time.perf_counter()
+                    rd = L.bz3_b200_stage_lzp_decode(st.handle, want.ctypes.data_as(u8p), rw, back.ctypes.data_as(u8p), cap)
+                    td = time.perf_counter() - t0
+                    okd = rd == n and bytes(back[:n]) == bytes(data)
+                    dw = np.zeros(cap + 64, np.uint8)   # truncated input: same verdict and bytes as the oracle
+                    dg = np.zeros(cap + 64, np.uint8)
+                    sw = O.orc_lzp_decode(want.ctypes.data_as(u8p), rw // 2, dw.ctypes.data_as(u8p), cap, lp)
+                    sg = L.bz3_b200_stage_lzp_decode(st.handle, want.ctypes.data_as(u8p), rw // 2, dg.ctypes.data_as(u8p), cap)
+                    okd = okd and sg == sw and (sw <= 0 or bytes(dg[:sw]) == bytes(dw[:sw]))
+                rec["v%d" % v] = {"enc_ok": bool(ok), "enc_ms": te * 1e3, "dec_ok": bool(okd), "dec_ms": td * 1e3}
+                result["ok"] = result["ok"] and bool(ok) and bool(okd)
+                print("  lzp v%d %-10s enc %-5s %8.2f ms (%7.1f MB/s)   dec %-5s %8.2f ms   lzp_size %d" % (
+                    v, name, "OK" if ok else "FAIL", te * 1e3, n / te / 1e6, "OK" if okd else "FAIL", td * 1e3, rw), flush=True)
+            L.bz3_b200_set_variant(st.handle, LZP, 0)
+            result["lzp"][name] = rec
         # whole-block round trip with the new kernels selected through the public block API
         blk = np.ascontiguousarray(sets[0][1][: min(n, 1 << 20)])
         enc_o, r_o, e_o = refs.oracle_encode_block(bytes(blk), max(n, 1 << 20))
