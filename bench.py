@@ -243,6 +243,7 @@ def run_b200_arm(args, rank, world, local_rank):
     total = sum(len(b) for b in blocks)
     states = [bzip3_b200.Bz3State(bs) for _ in blocks]
     hs = (C.c_void_p * nb)(*[s.handle for s in states])
+    cm_variants = (L.bz3_b200_get_variant(states[0].handle, 5 + 100), L.bz3_b200_get_variant(states[0].handle, 5 + 200))
     sizes = (C.c_int32 * nb)(*[len(b) for b in blocks])
     osz = (C.c_int32 * nb)(*[len(b) for b in blocks])
     enc_sizes = (C.c_int32 * nb)()
@@ -392,7 +393,13 @@ def run_b200_arm(args, rank, world, local_rank):
         cm_enc_ms = stage_total(stage_enc, "cm") / (nb * args.steps)
         avg_n = total / nb
         avg_c = sum(int(e) for e in enc_sizes) / nb
-        dom = "cm_decode_tree_kernel" if cm_dec_ms >= cm_enc_ms else "cm_encode_chunked_kernel"
+        dec_names = {0: "cm_decode_tree_kernel", 1: "cm_decode_single_kernel", 3: "cm_decode_paths_kernel",
+                     4: "cm_decode_lanes_kernel", 5: "cm_decode_paths2_kernel", 6: "cm_decode_walkers_kernel"}
+        enc_names = {1: "cm_encode_single_kernel", 2: "cm_encode_chunked_kernel<1>", 4: "cm_encode_chunked_kernel<2>",
+                     6: "cm_encode_chunked_kernel<3>"}
+        v_enc, v_dec = cm_variants
+        dom = (dec_names.get(v_dec, "cm_decode_tree_kernel") if cm_dec_ms >= cm_enc_ms
+               else enc_names.get(v_enc, "cm_encode_chunked_kernel<0>"))
         dom_ms = max(cm_dec_ms, cm_enc_ms)
         dom_bytes = avg_n + avg_c  # the coder reads/writes the BWT bytes once and the payload once
         achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0

@@ -859,6 +859,11 @@ extern "C" BZIP3_API void bz3_b200_debug_cm_profile(unsigned long long* out16) {
     cudaMemcpyFromSymbol(out16, g_cm_prof, sizeof(unsigned long long) * 48);
 }
 #endif
+BZIP3_API int bz3_b200_get_variant(struct bz3_state* s, int stage) {
+    if (stage == BZ3_STAGE_CM + 100) return s->cm_enc;
+    if (stage == BZ3_STAGE_CM + 200) return s->cm_dec;
+    return (stage >= 0 && stage < BZ3_STAGE_COUNT) ? s->variant[stage] : -1;
+}
 BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant) {
     if (stage >= 0 && stage < BZ3_STAGE_COUNT) s->variant[stage] = variant;
     // the entropy stage has separate encoder / decoder selections: BZ3_STAGE_CM sets both (0 = defaults),
