@@ -20,6 +20,11 @@ CASES = synth.edge_cases()
 IDS = [c[0] for c in CASES]
 BS = 1 << 20
 
+# Kernel variants that were written after the last GPU session of round 1: validated on the CPU thread-block
+# emulator (tests/test_emu_kernels.py) but never yet executed on hardware.  They are opt-in here until
+# `BZ3_B200_TEST_NEW=1 python -m pytest tests -m gpu` (and tools/eval_variants.py) has passed on a B200 once.
+NEW_UNTIMED = os.environ.get("BZ3_B200_TEST_NEW", "") not in ("", "0")
+
 
 def arr(b):
     return np.frombuffer(bytes(b), dtype=np.uint8).copy()
@@ -84,6 +89,8 @@ def test_stage_rle(st, O, name, data):
 @pytest.mark.parametrize("variant", [0, 1, 2], ids=["warp", "single", "warp_windows_in_flight"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_stage_lzp(st, O, name, data, variant):
+    if variant == 2 and not NEW_UNTIMED:
+        pytest.skip("LZP variant 2 has not run on a GPU yet (set BZ3_B200_TEST_NEW=1)")
     st.L.bz3_b200_set_variant(st.handle, 3, variant)
     try:
         _check_lzp(st, O, data)
@@ -161,6 +168,8 @@ def test_stage_cm(st, O, name, data, variant):
     n = len(a)
     if variant in (1, 2) and n > 120_000:
         pytest.skip("cross-check kernel variants kept to small inputs")
+    if variant == 6 and not NEW_UNTIMED:
+        pytest.skip("CM variant 6 has not run on a GPU yet (set BZ3_B200_TEST_NEW=1)")
     pad = np.zeros(n + 16, np.uint8)
     pad[:n] = a
     want = np.zeros(2 * n + 64, np.uint8)
