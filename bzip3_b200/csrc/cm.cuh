@@ -744,6 +744,105 @@ BZ_D void cm_dec_model_thread(u16* cm_smem, u32* ptab, volatile u32* vbyte, s32 
     }
 }
 
+// Same model thread with fewer instructions per byte (variant 7).  On B200 the walker kernel is bound by
+// instruction issue, not by its latency chain: every scheduler hosts two walker warps and two model warps, and
+// the loop above is ~110 SASS instructions per byte.  Here the update outcome is computed only for the
+// hypothesised byte and only by the threads on its path (eight of 255, so half of the warps skip the block
+// entirely); the outcome for any other byte is computed after the fact, on a miss, again only on the path.
+template <int LAYOUT, int PROTO>
+BZ_D void cm_dec_model_thread_slim(u16* cm_smem, u32* ptab, volatile u32* vbyte, s32 n, const int node) {
+    const int sh = node ? 8 - (31 - __clz(node)) : 8;                 // (256|byte) >> sh == node <=> on the path
+    u16* const q0 = cm_smem + node;
+    u16* const c1col = cm_smem + kCmC0 + node;                        // + prev * 256
+    u16* const rows = cm_smem + kCmC0 + kCmC1 + (2 * node) * 17;      // + flag * 17 + cell
+    int prev1 = 0, prev2 = 0;
+    u32 run = 0;
+    u16* q1 = c1col;
+    u32 a = *q0, b = *q1, d = *q1;
+    u32 lo = 0, hi = 0;
+    u16* cell = rows;
+    bool have = false;   // ptab of the current byte was already produced by the speculation
+    for (s32 i = 0; i < n; i++) {
+        if (!have) {
+            run = (prev1 == prev2) ? run + 1 : 0;
+            const int flag = run > 2;
+            const u32 p = ((a + b) * 7 + d + d) >> 4;
+            cell = rows + flag * 17 + (p >> 12);
+            lo = cell[0];
+            hi = cell[1];
+            const int sse = (int)lo + ((((int)hi - (int)lo) * (int)(p & 4095)) >> 12);
+            cm_ptab_put<LAYOUT>(ptab, (i & 1) * 256 + node, (u32)(sse * 3 + (int)p) << 14);
+            __syncthreads();   // ptab ready
+        }
+        // speculation: byte i == prev1
+        const u32 hyp = (u32)prev1;
+        const bool on_h = node != 0 && ((256u | hyp) >> sh) == (u32)node;
+        u32 a_s = a, b_s = b, nl = lo, nh = hi;   // counters as byte i == hyp would leave them
+        if (on_h) {
+            const u32 ones = ((hyp >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
+            a_s = cm_adapt_bf(a, ones, 2);
+            b_s = cm_adapt_bf(b, ones, 4);
+            nl = cm_adapt_bf(lo, ones, 6);
+            nh = cm_adapt_bf(hi, ones, 6);
+        }
+        const u32 run_s = run + 1u;   // run rule (src/libbz3.c:367-370) applied to (prev1, prev1)
+        const int flag_s = run_s > 2;
+        const u32 p_s = ((a_s + b_s) * 7 + b_s + b_s) >> 4;
+        u16* const cell_s = rows + flag_s * 17 + (p_s >> 12);
+        u32 lo_s = cell_s[0], hi_s = cell_s[1];
+        if (on_h) {   // the pending update of byte i is not in shared memory yet
+            const bool same = cell_s == cell, up = cell_s == cell + 1, dn = cell_s + 1 == cell;
+            lo_s = same ? nl : (up ? nh : lo_s);
+            hi_s = same ? nh : (dn ? nl : hi_s);
+        }
+        {
+            const int sse = (int)lo_s + ((((int)hi_s - (int)lo_s) * (int)(p_s & 4095)) >> 12);
+            cm_ptab_put<LAYOUT>(ptab, ((i + 1) & 1) * 256 + node, (u32)(sse * 3 + (int)p_s) << 14);
+        }
+        if (PROTO == 0) {
+            __syncthreads();   // byte ready
+        } else {
+            if (!__syncthreads_or(0))
+                if (!__syncthreads_or(0)) __syncthreads();
+        }
+        const u32 byte = vbyte[i & 1];
+        have = byte == hyp;   // uniform across the CTA
+        if (have) {
+            if (on_h) {   // (C) learn byte i
+                *q0 = (u16)a_s;
+                *q1 = (u16)b_s;
+                cell[0] = (u16)nl;
+                cell[1] = (u16)nh;
+            }
+            a = a_s;
+            b = b_s;
+            d = b_s;
+            lo = lo_s;
+            hi = hi_s;
+            cell = cell_s;
+            run = run_s;
+            prev2 = prev1;   // == byte
+        } else {
+            u32 na = a, nb = b;
+            if (node != 0 && ((256u | byte) >> sh) == (u32)node) {   // (C) learn byte i
+                const u32 ones = ((byte >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
+                na = cm_adapt_bf(a, ones, 2);
+                nb = cm_adapt_bf(b, ones, 4);
+                *q0 = (u16)na;
+                *q1 = (u16)nb;
+                cell[0] = (u16)cm_adapt_bf(lo, ones, 6);
+                cell[1] = (u16)cm_adapt_bf(hi, ones, 6);
+            }
+            a = na;
+            d = nb;                       // this byte's order-1 counter is the next byte's prev2 counter
+            prev2 = prev1;
+            prev1 = (int)byte;
+            q1 = c1col + prev1 * 256;
+            b = *q1;                      // after the store above in program order
+        }
+    }
+}
+
 // ---- tree-parallel decoder ---------------------------------------------------------------------
 // Decoding is one dependent chain: the next context depends on the bit just decoded.  What does not
 // depend on the bits of the current byte is the probability of every one of the 255 tree nodes (no node
@@ -1728,6 +1827,7 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
     S.prevb = byte;
 }
 
+template <int SLIM>
 __global__ void __launch_bounds__(kCmDecW6Threads, 1) cm_decode_walkers_kernel(const u8* __restrict__ in, s32 insize,
                                                                               u8* __restrict__ out, s32 n) {
     BZ_DYN_SMEM(u16, cm_smem);
@@ -1741,7 +1841,8 @@ __global__ void __launch_bounds__(kCmDecW6Threads, 1) cm_decode_walkers_kernel(c
     for (int k = tid; k < 2048; k += kCmDecW6Threads) scode[k] = (k < insize) ? in[k] : 0;
     if (tid >= 256) {
         __syncthreads();
-        cm_dec_model_thread<1, 1>(cm_smem, ptab, pub + 16, n, tid - 256);
+        if (SLIM) cm_dec_model_thread_slim<1, 1>(cm_smem, ptab, pub + 16, n, tid - 256);
+        else cm_dec_model_thread<1, 1>(cm_smem, ptab, pub + 16, n, tid - 256);
         return;
     }
     // ---------------------------------------------------------------------- walker: leaf v = tid
@@ -1802,7 +1903,8 @@ inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecLanesSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecP2SmemBytes));
-    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_walkers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_walkers_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes));
+    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_walkers_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes));
     return cudaSuccess;
 }
 #endif
