@@ -261,7 +261,7 @@ cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, i
 // (cross-check), 2 chunked with the whole-byte exact tier (cross-check), 4 chunked with the one-multiply
 // coder lane (two-tier), 6 chunked with the one-multiply coder lane, single tier, software pipelined.  Decoder: 0 tree kernel with a serial chain warp, 1 single lane, 3 all-paths (first edition),
 // 4 tree kernel with the lane-parallel chain warp, 5 all-paths with one multiply per level, 6 walker warps
-// (the all-paths walk of 5) next to the model threads of 0/4, 7 = 6 with the slim model-thread loop.
+// (the all-paths walk of 5) next to the model threads of 0/4, 7 = 6 with the slim model-thread loop, 8 = 7 with walker warps that stop after three levels when the code is not in their eighth.
 // Defaults can be overridden per process with BZ3_B200_CM_ENC / BZ3_B200_CM_DEC (tuning, tests).
 constexpr int kCmEncDefault = 0;
 constexpr int kCmDecDefault = 0;
@@ -301,9 +301,11 @@ cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s
     else if (s->cm_dec == 5)
         cm_decode_paths2_kernel<<<1, kCmDecP2Threads, kCmDecP2SmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else if (s->cm_dec == 6)
-        cm_decode_walkers_kernel<0><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        cm_decode_walkers_kernel<0, 0><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else if (s->cm_dec == 7)
-        cm_decode_walkers_kernel<1><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        cm_decode_walkers_kernel<1, 0><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+    else if (s->cm_dec == 8)
+        cm_decode_walkers_kernel<1, 1><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else
         cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     BZ_NOTE_LAUNCH();

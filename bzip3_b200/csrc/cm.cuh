@@ -1745,7 +1745,7 @@ struct CmWalkState {
     bool have;
 };
 
-template <int HALF>
+template <int HALF, int PRUNE>
 BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u32* ptab, u8* scode, volatile u32* pub,
                            SmemAddr pub_a, const u8* __restrict__ in, const s32 insize, u8* __restrict__ out,
                            const u32 v) {
@@ -1759,10 +1759,32 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
         const u32 mm[8] = {lds_u32<HB>(K.pa[0]), lds_u32<HB>(K.pa[1]), lds_u32<HB>(K.pa[2]), lds_u32<HB>(K.pa[3]),
                            lds_u32<HB>(K.pa[4]), lds_u32<HB>(K.pa[5]), lds_u32<HB>(K.pa[6]), lds_u32<HB>(K.pa[7])};
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 3; k++) {
             const u64 w = cm_mul_wide(rk[k], mm[k]);
             rk[k + 1] = (u32)(w >> 32);
             zmin = min(zmin, (u32)w);
+        }
+        // PRUNE: the 32 lanes of a walker warp share the first three branches, so after three levels the whole
+        // warp knows (uniformly, no vote) whether the code lies in its eighth of the interval at all; seven of
+        // the eight walker warps stop here and free their issue slots.  (If a shift was due in these levels
+        // the test may fail for every warp -- then nobody wins and the byte is redone serially, as it would be
+        // anyway.)
+        bool alive = true;
+        if (PRUNE) {
+            const u32 a3 = S.low + (K.zk[0] & (rk[0] - rk[1])) + (K.zk[1] & (rk[1] - rk[2])) + (K.zk[2] & (rk[2] - rk[3]));
+            alive = (S.code - a3) <= rk[3];
+        }
+        if (alive) {
+#pragma unroll
+            for (int k = 3; k < 8; k++) {
+                const u64 w = cm_mul_wide(rk[k], mm[k]);
+                rk[k + 1] = (u32)(w >> 32);
+                zmin = min(zmin, (u32)w);
+            }
+        } else {
+            zmin = 0u;   // not a candidate
+#pragma unroll
+            for (int k = 3; k < 8; k++) rk[k + 1] = 0u;
         }
     }
     u32 acc = 0;
@@ -1827,7 +1849,7 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
     S.prevb = byte;
 }
 
-template <int SLIM>
+template <int SLIM, int PRUNE>
 __global__ void __launch_bounds__(kCmDecW6Threads, 1) cm_decode_walkers_kernel(const u8* __restrict__ in, s32 insize,
                                                                               u8* __restrict__ out, s32 n) {
     BZ_DYN_SMEM(u16, cm_smem);
@@ -1886,8 +1908,8 @@ __global__ void __launch_bounds__(kCmDecW6Threads, 1) cm_decode_walkers_kernel(c
     S.prevb = 0;
     const SmemAddr pub_a = smem_addr_of(pub);
     for (s32 i = 0; i < n; i += 2) {
-        cm_dec_walk_step<0>(K, S, i, ptab, scode, pub, pub_a, in, insize, out, v);
-        if (i + 1 < n) cm_dec_walk_step<1>(K, S, i + 1, ptab, scode, pub, pub_a, in, insize, out, v);
+        cm_dec_walk_step<0, PRUNE>(K, S, i, ptab, scode, pub, pub_a, in, insize, out, v);
+        if (i + 1 < n) cm_dec_walk_step<1, PRUNE>(K, S, i + 1, ptab, scode, pub, pub_a, in, insize, out, v);
     }
 }
 
@@ -1903,8 +1925,9 @@ inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecLanesSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_paths2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecP2SmemBytes));
-    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_walkers_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes));
-    BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_walkers_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes));
+    BZ_CUDA_TRY((cudaFuncSetAttribute(cm_decode_walkers_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes)));
+    BZ_CUDA_TRY((cudaFuncSetAttribute(cm_decode_walkers_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes)));
+    BZ_CUDA_TRY((cudaFuncSetAttribute(cm_decode_walkers_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes)));
     return cudaSuccess;
 }
 #endif

@@ -65,11 +65,15 @@ EXPORT int emu_cm_decode(int variant, const uint8_t* in, int32_t insize, uint8_t
             break;
         case 6:
             b.x = kCmDecW6Threads;
-            emu::launch(g, b, kCmDecW6SmemBytes, [&] { cm_decode_walkers_kernel<0>(in, insize, out, n); });
+            emu::launch(g, b, kCmDecW6SmemBytes, [&] { cm_decode_walkers_kernel<0, 0>(in, insize, out, n); });
             break;
         case 7:
             b.x = kCmDecW6Threads;
-            emu::launch(g, b, kCmDecW6SmemBytes, [&] { cm_decode_walkers_kernel<1>(in, insize, out, n); });
+            emu::launch(g, b, kCmDecW6SmemBytes, [&] { cm_decode_walkers_kernel<1, 0>(in, insize, out, n); });
+            break;
+        case 8:
+            b.x = kCmDecW6Threads;
+            emu::launch(g, b, kCmDecW6SmemBytes, [&] { cm_decode_walkers_kernel<1, 1>(in, insize, out, n); });
             break;
         case 5:
             b.x = kCmDecP2Threads;

@@ -65,10 +65,10 @@ def bwt_of(data: np.ndarray) -> np.ndarray:
 def cm_inputs():
     rng = np.random.default_rng(99)
     cases = [(name, arr(d)[:3000]) for name, d in synth.edge_cases() if len(d) > 0]
-    cases.append(("bwt_zipf_24k", bwt_of(synth.zipf_text(24 << 10, seed=7))))
-    cases.append(("bwt_source_16k", bwt_of(synth.source_corpus(16 << 10, seed=8))))
+    cases.append(("bwt_zipf_12k", bwt_of(synth.zipf_text(12 << 10, seed=7))))
+    cases.append(("bwt_source_10k", bwt_of(synth.source_corpus(10 << 10, seed=8))))
     cases.append(("random_6k", rng.integers(0, 256, 6000, dtype=np.uint8)))
-    cases.append(("runs_20k", np.repeat(rng.integers(0, 4, 200, dtype=np.uint8), 100)))
+    cases.append(("runs_8k", np.repeat(rng.integers(0, 4, 80, dtype=np.uint8), 100)))
     cases.append(("one_byte", np.array([65], np.uint8)))
     return cases
 
@@ -77,7 +77,7 @@ CM_CASES = cm_inputs()
 CM_IDS = [c[0] for c in CM_CASES]
 
 ENC_VARIANTS = [0, 1, 2, 4, 6]
-DEC_VARIANTS = [0, 1, 3, 4, 5, 6, 7]
+DEC_VARIANTS = [0, 1, 3, 4, 5, 6, 7, 8]
 
 
 @pytest.mark.parametrize("variant", ENC_VARIANTS)
@@ -85,6 +85,8 @@ DEC_VARIANTS = [0, 1, 3, 4, 5, 6, 7]
 def test_cm_encode_kernels(name, data, variant):
     E, O = emu(), refs.oracle()
     n = len(data)
+    if variant in (1, 2) and n > 8000:
+        pytest.skip("cross-check kernel variants: small inputs only (suite time)")
     want = np.zeros(2 * n + 64, np.uint8)
     got = np.zeros(2 * n + 64, np.uint8)
     rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
@@ -98,6 +100,8 @@ def test_cm_encode_kernels(name, data, variant):
 def test_cm_decode_kernels(name, data, variant):
     E, O = emu(), refs.oracle()
     n = len(data)
+    if variant in (1, 3, 5) and n > 8000:
+        pytest.skip("older kernel variants: small inputs only (suite time)")
     enc = np.zeros(2 * n + 64, np.uint8)
     r = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(enc))
     # the whole stream, a truncated stream (read_in() past the end adds -1) and an empty one
@@ -115,7 +119,7 @@ def test_cm_decode_kernels(name, data, variant):
 def test_cm_kernels_other_schedules(schedule):
     """Same result when the fibers are scheduled in descending or pseudo-random order."""
     E, O = emu(), refs.oracle()
-    data = CM_CASES[CM_IDS.index("bwt_zipf_24k")][1][:8000]
+    data = CM_CASES[CM_IDS.index("bwt_zipf_12k")][1][:5000]
     n = len(data)
     want = np.zeros(2 * n + 64, np.uint8)
     rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
