@@ -50,6 +50,7 @@ struct Fiber {
     char* stack = nullptr;
     Dim3 tid;
     bool done = false;
+    const void* waiting_on = nullptr;    // barrier / collective slot this fiber sleeps on (not scheduled meanwhile)
     std::map<uint32_t, unsigned> phase;  // per-mask count of warp collectives executed
 };
 
@@ -90,10 +91,23 @@ inline int pick_next() {
     }
     for (int k = 1; k <= n; k++) {
         int i = g_schedule == 1 ? ((start - k) % n + n) % n : (start + k) % n;
-        if (!c.fibers[i].done) return i;
+        if (!c.fibers[i].done && !c.fibers[i].waiting_on) return i;
     }
     return -1;
 }
+
+inline void wake_all(const void* obj) {
+    for (auto& f : g_cta->fibers)
+        if (f.waiting_on == obj) f.waiting_on = nullptr;
+}
+
+[[noreturn]] inline void deadlock(const char* what) {
+    fprintf(stderr, "[cta_emu] deadlock: every live thread sleeps (%s)\n", what);
+    abort();
+}
+
+// sleep until somebody calls wake_all(obj)
+inline void sleep_on(const void* obj, const char* what);
 
 inline void yield() {
     Cta& c = *g_cta;
@@ -106,10 +120,23 @@ inline void yield() {
     emu_switch(&from->sp, g_cur->sp);
 }
 
+inline void sleep_on(const void* obj, const char* what) {
+    Cta& c = *g_cta;
+    g_cur->waiting_on = obj;
+    const int nxt = pick_next();
+    if (nxt < 0) deadlock(what);
+    Fiber* from = g_cur;
+    c.cur = nxt;
+    g_cur = &c.fibers[nxt];
+    c.switches++;
+    emu_switch(&from->sp, g_cur->sp);
+}
+
 [[noreturn]] inline void fiber_exit() {
     Cta& c = *g_cta;
     g_cur->done = true;
     c.live--;
+    for (auto& f : c.fibers) f.waiting_on = nullptr;   // an exit can complete a barrier: let sleepers re-check
     const int nxt = pick_next();
     void* dummy;
     if (nxt < 0) {
@@ -136,7 +163,6 @@ inline unsigned bar_sync_impl(int id, unsigned count, unsigned pred, bool wait) 
     const unsigned gen = b.gen;
     b.arrived++;
     b.orv |= pred;
-    unsigned long long spins = 0;
     for (;;) {
         const unsigned need = count ? count : c.live;
         if (b.gen != gen) break;
@@ -145,14 +171,11 @@ inline unsigned bar_sync_impl(int id, unsigned count, unsigned pred, bool wait) 
             b.last_or = b.orv;
             b.orv = 0;
             b.gen++;
+            wake_all(&b);
             break;
         }
         if (!wait) return 0;
-        yield();
-        if (++spins > 50000000ull) {
-            fprintf(stderr, "[cta_emu] deadlock: barrier %d never completes (arrived %u of %u)\n", id, b.arrived, need);
-            abort();
-        }
+        sleep_on(&b, "barrier");
     }
     return b.last_or;
 }
@@ -184,14 +207,9 @@ inline auto warp_collective(uint32_t mask, uint64_t mine, R reader) -> decltype(
     }
     s.val[lane] = mine;
     s.arrived |= bit;
-    // lanes of the mask that already exited can never arrive: treat as a bug
-    while ((s.arrived & mask) != mask) {
-        yield();
-        if (++spins > 50000000ull) {
-            fprintf(stderr, "[cta_emu] deadlock in warp collective: warp %u mask %08x arrived %08x\n", warp_of(f), mask, s.arrived);
-            abort();
-        }
-    }
+    if ((s.arrived & mask) == mask) wake_all(&s);
+    // lanes of the mask that already exited can never arrive: that is a bug and ends in the deadlock report
+    while ((s.arrived & mask) != mask) sleep_on(&s, "warp collective");
     auto r = reader(s.val);
     s.consumed |= bit;
     if ((s.consumed & mask) == mask) {
