@@ -257,11 +257,14 @@ cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, i
     return unbwt(s->stream, d_in, n, idx, d_out, B, status);
 }
 
-// Entropy-stage kernels.  Encoder: 0 chunked pipeline with the select/mul.hi coder lane, 1 single lane
-// (cross-check), 2 chunked with the whole-byte exact tier (cross-check), 4 chunked with the one-multiply
-// coder lane (two-tier), 6 chunked with the one-multiply coder lane, single tier, software pipelined.  Decoder: 0 tree kernel with a serial chain warp, 1 single lane, 3 all-paths (first edition),
-// 4 tree kernel with the lane-parallel chain warp, 5 all-paths with one multiply per level, 6 walker warps
-// (the all-paths walk of 5) next to the model threads of 0/4, 7 = 6 with the slim model-thread loop, 8 = 7 with walker warps that stop after three levels when the code is not in their eighth.
+// Entropy-stage kernels.
+//   encoder  0 chunked pipeline, select/mul.hi coder lane        1 single lane (cross-check)
+//            2 chunked, whole-byte exact tier (cross-check)      4 chunked, one-multiply coder lane, two-tier
+//            6 chunked, one-multiply coder lane, branch-free byte + resume at the first event
+//   decoder  0 tree kernel, serial chain warp                    1 single lane (cross-check)
+//            3 all paths, first edition                          4 tree kernel, lane-parallel chain warp
+//            5 all paths, one multiply per level                 6 walker warps (walk of 5) + model threads of 0/4
+//            7 = 6 with the slim model-thread loop               8 = 7, walker warps stop after three levels
 // Defaults can be overridden per process with BZ3_B200_CM_ENC / BZ3_B200_CM_DEC (tuning, tests).
 constexpr int kCmEncDefault = 0;
 constexpr int kCmDecDefault = 0;
