@@ -1743,6 +1743,9 @@ struct CmWalkState {
     u32 low, range, code, prevb;
     s32 ip, wlo;
     bool have;
+#ifdef BZ_CM_PROFILE
+    unsigned long long _acc[8], _t0, _t1;
+#endif
 };
 
 template <int HALF, int PRUNE>
@@ -1750,6 +1753,7 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
                            SmemAddr pub_a, const u8* __restrict__ in, const s32 insize, u8* __restrict__ out,
                            const u32 v) {
     if (!S.have) __syncthreads();   // B1: ptab ready (skipped when the speculation of the model threads hit)
+    BZ_SPROF_AFTER_BAR(S, 0, ptab + HALF * 512 + 2);
     constexpr int HB = HALF * 2048;   // byte offset of this byte's half of ptab
     constexpr int PB = HALF * 32;     // byte offset of this byte's publication slot
     u32 rk[9];
@@ -1800,7 +1804,11 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
         sts_u32<PB + 8>(pub_a, r8);
         sts_u32<64 + HALF * 4>(pub_a, v);   // the byte slot the model threads read
     }
-    if (!__syncthreads_or(ok ? 1 : 0)) {   // B2: byte and state published -- or nobody passed the fast test
+    BZ_SPROF(S, 1);
+    const int won1 = __syncthreads_or(ok ? 1 : 0);   // B2: byte and state published -- or nobody passed the fast test
+    BZ_SPROF_AFTER_BAR(S, 2, pub + HALF * 8);
+    if (!won1) {
+        BZ_SCOUNT(S, 5);
         bool ok2 = false;
         if (cand) {   // reference's shift test on my own path
             u32 al = S.low, tmin = 0xFFFFFFFFu;
@@ -1818,6 +1826,7 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
             }
         }
         if (!__syncthreads_or(ok2 ? 1 : 0)) {
+            BZ_SCOUNT(S, 6);
             if (v == 0) {   // exact serial decoder for this byte (reference loop)
                 u32 flow = S.low, frange = S.range, fcode = S.code;
                 s32 fip = S.ip;
@@ -1833,6 +1842,7 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
             S.code = pub[HALF * 8 + 3];
             S.ip = (s32)pub[HALF * 8 + 4];
         }
+        BZ_SPROF_AFTER_BAR(S, 3, pub + HALF * 8);
     }
     const u32 byte = lds_u32<PB + 0>(pub_a);
     S.low = lds_u32<PB + 4>(pub_a);
@@ -1847,6 +1857,7 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
     }
     S.have = byte == S.prevb;
     S.prevb = byte;
+    BZ_SPROF(S, 4);
 }
 
 template <int SLIM, int PRUNE>
@@ -1907,10 +1918,18 @@ __global__ void __launch_bounds__(kCmDecW6Threads, 1) cm_decode_walkers_kernel(c
     S.have = false;
     S.prevb = 0;
     const SmemAddr pub_a = smem_addr_of(pub);
+#ifdef BZ_CM_PROFILE
+    for (int k = 0; k < 8; k++) S._acc[k] = 0;
+    S._t0 = clock64();
+#endif
     for (s32 i = 0; i < n; i += 2) {
         cm_dec_walk_step<0, PRUNE>(K, S, i, ptab, scode, pub, pub_a, in, insize, out, v);
         if (i + 1 < n) cm_dec_walk_step<1, PRUNE>(K, S, i + 1, ptab, scode, pub, pub_a, in, insize, out, v);
     }
+#ifdef BZ_CM_PROFILE
+    if (v == 0)
+        for (int k = 0; k < 8; k++) g_cm_prof[36 + k] = S._acc[k];   // wait B1, walk, wait B2, slow path, tail, #slow, #serial
+#endif
 }
 
 #if defined(__CUDACC__)

@@ -44,7 +44,7 @@ def main():
                 p = prof()
                 rec["enc_v%d" % v] = {"stage1_busy": p[13] / n, "stage2_busy": p[14] / n, "coder_busy": p[15] / n,
                                       "exact_tier_cycles": p[32] / n, "exact_tier_bytes_frac": p[33] / n}
-            for v in (0, 4, 5):
+            for v in (0, 4, 5, 6, 7, 8):
                 L.bz3_b200_set_variant(st.handle, CM + 200, v)
                 back = np.zeros(n + 8, np.uint8)
                 L.bz3_b200_stage_cm_decode(st.handle, enc.ctypes.data_as(u8p), r, back.ctypes.data_as(u8p), n)
@@ -56,9 +56,12 @@ def main():
                 elif v == 4:
                     rec["dec_v4_chain"] = dict(zip(("wait_ptab", "round1_fast", "round1_exact", "round2_fast", "round2_exact",
                                                     "publish_wait_byte", "fb1_frac", "fb2_frac"), [x / n for x in p[16:24]]))
-                else:
+                elif v == 5:
                     rec["dec_v5_thread0"] = dict(zip(("predict", "wait_S1", "walk", "wait_S2", "fallback", "learn", "fallback_frac"),
                                                      [x / n for x in p[24:31]]))
+                else:
+                    rec["dec_v%d_walker0" % v] = dict(zip(("wait_B1", "walk", "wait_B2", "slow_path", "tail", "slow_frac",
+                                                           "serial_frac"), [x / n for x in p[36:43]]))
             L.bz3_b200_set_variant(st.handle, CM, 0)
             out[name] = rec
             print(name)
