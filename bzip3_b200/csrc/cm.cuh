@@ -1049,32 +1049,47 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_tree_kernel(const u8*
 // 8 suffixes.  A lane whose range dropped below 2^24 (necessary for a shift) also disqualifies itself; if
 // that was the true path nobody wins and the round is redone by the reference loop (cm_dec_exact_levels).
 
-// reference loop for `nlev` tree levels from `node` on (src/libbz3.c:452-476); uniform across the warp
-BZ_D u32 cm_dec_exact_levels(const u32* __restrict__ pt, u32 node, const int nlev, u32& low, u32& range, u32& code,
+// reference loop for `nlev` tree levels from `node` on (src/libbz3.c:452-476); uniform across the caller's lanes.
+// Serial, so written for the dependent-issue latencies measured on B200 (multiply 10, shared load 23, add/select
+// ~3.4): one mul.hi per level, both outcomes of the level formed next to the compare, and the multipliers of both
+// possible next nodes' children loaded one level ahead (the {M, -M} pairs of the two children of a node share one
+// 16-byte word), so no load sits on the recurrence  mul.hi -> add -> compare -> select.
+template <int NLEV>
+BZ_D u32 cm_dec_exact_levels(const u32* __restrict__ pt, u32 node, u32& low, u32& range, u32& code,
                              s32& ip, const s32 insize, const u8* __restrict__ scode) {
-    uint4 kids = *reinterpret_cast<const uint4*>(pt + 4 * node);   // children 2*node, 2*node+1: {M, -M, M, -M}
+    const uint4* pt4 = reinterpret_cast<const uint4*>(pt);   // pt4[n] = {M, -M} of nodes 2n and 2n+1
     u32 m = pt[2 * node];
-    for (int k = 0; k < nlev; k++) {
-        const u32 x = __umulhi(range, m);
-        const u32 mid = low + x;
+    uint4 kids = pt4[node];
+    u32 r = range, lo = low;   // absolute low, not code - low: a hostile stream may put the code below low
+#pragma unroll
+    for (int k = 0; k < NLEV; k++) {   // unrolled: a taken branch costs as much as the whole recurrence of a level
+        uint4 g0 = kids, g1 = kids;
+        if (node < 64) {   // children of both possible next nodes
+            g0 = pt4[2 * node];
+            g1 = pt4[2 * node + 1];
+        }
+        const u32 x = __umulhi(r, m);
+        const u32 mid = lo + x;
         const bool bit = code <= mid;
-        range = bit ? x : range - x - 1u;
-        low = bit ? low : mid + 1u;
+        r = bit ? x : r + ~x;        // x  |  range - x - 1
+        lo = bit ? lo : mid + 1u;
         node = node * 2 + (bit ? 1u : 0u);
         m = bit ? kids.z : kids.x;
-        if (node < 128) kids = *reinterpret_cast<const uint4*>(pt + 4 * node);
-        if (range < (1u << 24)) {   // necessary for the top bytes of low and high to agree
-            u32 high = low + range;
-            while ((low ^ high) < (1u << 24)) {
-                low <<= 8;
+        kids = bit ? g1 : g0;
+        if (r < (1u << 24)) {   // necessary for the top bytes of low and high to agree
+            u32 high = lo + r;
+            while ((lo ^ high) < (1u << 24)) {
+                lo <<= 8;
                 high = (high << 8) | 0xFFu;
                 const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;   // read_in() past the end adds -1
                 ip += (ip < insize);
                 code = (code << 8) + add;
             }
-            range = high - low;
+            r = high - lo;
         }
     }
+    low = lo;
+    range = r;
     return node;
 }
 
@@ -1194,7 +1209,7 @@ BZ_D void cm_dec_lanes_step(const CmLaneConsts& K, CmChainState& S, const s32 i,
 #if defined(BZ_EMU_STATS)
             if (tid == 0) g_emu_stats[0]++;
 #endif
-            node = cm_dec_exact_levels(pt, 1u, 5, S.low, S.range, S.code, S.ip, insize, scode);
+            node = cm_dec_exact_levels<5>(pt, 1u, S.low, S.range, S.code, S.ip, insize, scode);
             BZ_SPROF(S, 2);
         }
     }
@@ -1233,7 +1248,7 @@ BZ_D void cm_dec_lanes_step(const CmLaneConsts& K, CmChainState& S, const s32 i,
 #if defined(BZ_EMU_STATS)
             if (tid == 0) g_emu_stats[1]++;
 #endif
-            node = cm_dec_exact_levels(pt, node, 3, S.low, S.range, S.code, S.ip, insize, scode);
+            node = cm_dec_exact_levels<3>(pt, node, S.low, S.range, S.code, S.ip, insize, scode);
             BZ_SPROF(S, 4);
         }
     }
@@ -1669,7 +1684,7 @@ __global__ void __launch_bounds__(kCmDecP2Threads, 1) cm_decode_paths2_kernel(co
                     if (tid == 0) {   // exact serial decoder for this byte (reference loop)
                         u32 flow = low, frange = range, fcode = code;
                         s32 fip = ip;
-                        const u32 nd = cm_dec_exact_levels(ptab, 1u, 8, flow, frange, fcode, fip, insize, scode);
+                        const u32 nd = cm_dec_exact_levels<8>(ptab, 1u, flow, frange, fcode, fip, insize, scode);
                         pub[0] = nd & 255u;
                         pub[1] = flow;
                         pub[2] = frange;
@@ -1830,7 +1845,7 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
             if (v == 0) {   // exact serial decoder for this byte (reference loop)
                 u32 flow = S.low, frange = S.range, fcode = S.code;
                 s32 fip = S.ip;
-                const u32 nd = cm_dec_exact_levels(ptab + HALF * 512, 1u, 8, flow, frange, fcode, fip, insize, scode);
+                const u32 nd = cm_dec_exact_levels<8>(ptab + HALF * 512, 1u, flow, frange, fcode, fip, insize, scode);
                 pub[HALF * 8 + 0] = nd & 255u;
                 pub[HALF * 8 + 1] = flow;
                 pub[HALF * 8 + 2] = frange;
