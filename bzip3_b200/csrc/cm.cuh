@@ -458,6 +458,93 @@ BZ_D void rc_byte3(u32& low, u32& range, u64& w, s32& op, const u32 sym, const u
     w = ww;
 }
 
+// The coder lane of MODE 3 over one chunk.  Two nested loops on purpose: the inner loop runs over bytes without an
+// event and its only taken branch is the back-edge (a taken branch costs ~20 cycles, a skipped-over block is a
+// taken branch); an event leaves it through a rarely taken exit, is handled, and the inner loop is re-entered.
+BZ_D void rc_lane3(const u32* __restrict__ pw, const u8* __restrict__ sb, const s32 len, u32& low, u32& range, s32& op,
+                   u8* __restrict__ out) {
+    const uint4* pv = reinterpret_cast<const uint4*>(pw);
+    s32 k = 0;
+    uint4 a = pv[0], b = pv[1];   // multipliers of byte k
+    u32 sym = sb[0];
+    u32 l = low, r = range;
+    u64 w = cm_mul_wide(r, a.x);  // product of the first decision of byte k
+    u32 rk[9];
+    for (;;) {
+        bool event = false;
+#pragma unroll 2
+        while (k < len) {
+            const s32 kn = (k + 1 < len) ? k + 1 : k;   // the last byte re-reads itself; that product is unused
+            const uint4 na = pv[2 * kn], nb = pv[2 * kn + 1];
+            const u32 nsym = sb[kn];
+            const u32 m[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, na.x};
+            u32 ln = l, tmin = 0xFFFFFFFFu, zmin = 0xFFFFFFFFu;
+            u64 ww = w;
+            rk[0] = r;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const u32 rn = (u32)(ww >> 32);
+                zmin = min(zmin, (u32)ww);
+                ww = cm_mul_wide(rn, m[j + 1]);
+                if (!(sym & (0x80u >> j))) ln += rk[j] - rn;
+                rk[j + 1] = rn;
+                tmin = min(tmin, ln ^ (ln + rn));
+            }
+            if (tmin < (1u << 24) || zmin == 0u) {
+                event = true;
+                break;
+            }
+            l = ln;
+            r = rk[8];
+            w = ww;
+            a = na;
+            b = nb;
+            sym = nsym;
+            k++;
+        }
+        if (!event) break;
+        // byte k had an event: find the first decision with one (cheap: the ranges are known) ...
+        int kf = 0;
+        for (; kf < 8; kf++) {
+            u32 rb = rk[0], ra = rk[1];   // rk[kf], rk[kf + 1] without dynamic register indexing
+#pragma unroll
+            for (int j = 1; j < 8; j++) {
+                rb = (j == kf) ? rk[j] : rb;
+                ra = (j == kf) ? rk[j + 1] : ra;
+            }
+            const bool bit = (sym & (0x80u >> kf)) != 0;
+            const u32 ln = bit ? l : l + (rb - ra);
+            if (((ln ^ (ln + ra)) < (1u << 24)) || (u32)(rb * pw[8 * k + kf]) == 0u) break;   // lo32 of the product
+            l = ln;
+        }
+        // ... the decisions before it stand; from it on the byte is finished with the reference loop
+        u32 rr = rk[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) rr = (j == kf) ? rk[j] : rr;
+        u32 high = l + rr;
+        for (int j = kf; j < 8; j++) {   // src/libbz3.c:388-416
+            const bool bit = (sym & (0x80u >> j)) != 0;
+            const u32 mk = pw[8 * k + j];
+            const u32 x = __umulhi(high - l, bit ? mk : 0u - mk);
+            if (bit) high = l + x; else l += x + 1u;
+            while ((l ^ high) < (1u << 24)) {
+                out[op++] = (u8)(l >> 24);
+                l <<= 8;
+                high = (high << 8) | 0xFFu;
+            }
+        }
+        r = high - l;
+        k++;
+        if (k >= len) break;
+        a = pv[2 * k];
+        b = pv[2 * k + 1];
+        sym = sb[k];
+        w = cm_mul_wide(r, a.x);
+    }
+    low = l;
+    range = r;
+}
+
 // Three-stage chunk pipeline (one __syncthreads per chunk, no polling):
 //   warp 0, lanes 0..7  stage 1: c0 / c1 counters of tree depth `lane`  -> mixed probability p (16 bit)
 //   warp 2, lanes 0..7  stage 2: SSE rows c2 of depth `lane`            -> P << 14
@@ -501,8 +588,11 @@ __global__ void __launch_bounds__(kCmEncThreads, 1) cm_encode_chunked_kernel(con
                 __syncwarp();
                 if (lane < 8) {
                     u16* pm = pmid + (it & 1) * (kCmEncChunk * 8) + lane;
+                    int symn = sb[0];   // MODE 3: the next symbol is read one byte ahead (its load cannot pass the stores below)
+#pragma unroll(MODE == 3 ? 2 : 1)
                     for (s32 k = 0; k < len; k++) {
-                        const int sym = sb[k];
+                        const int sym = (MODE == 3) ? symn : (int)sb[k];
+                        if (MODE == 3) symn = sb[(k + 1 < len) ? k + 1 : k];
                         const int node = top | (sym >> sh_node);
                         const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
                         u16* q0 = c0 + node;
@@ -524,9 +614,16 @@ __global__ void __launch_bounds__(kCmEncThreads, 1) cm_encode_chunked_kernel(con
                 const u8* sb = sbytes + (ch % 3) * kCmEncChunk;
                 const u16* pm = pmid + (ch & 1) * (kCmEncChunk * 8) + lane;
                 u32* pb = pbuf + (ch & 1) * (kCmEncChunk * 8) + lane;
+                int symn = sb[0], pn = pm[0];   // MODE 3: symbol and mixed probability are read one byte ahead
+#pragma unroll(MODE == 3 ? 2 : 1)
                 for (s32 k = 0; k < len; k++) {
-                    const int sym = sb[k];
-                    const int p = pm[k * 8];
+                    const int sym = (MODE == 3) ? symn : (int)sb[k];
+                    const int p = (MODE == 3) ? pn : (int)pm[k * 8];
+                    if (MODE == 3) {
+                        const s32 kn = (k + 1 < len) ? k + 1 : k;
+                        symn = sb[kn];
+                        pn = pm[kn * 8];
+                    }
                     run = (prev1 == prev2) ? run + 1 : 0;           // run flag of this byte (src/libbz3.c:367-372)
                     const int flag = run > 2;
                     const int node = top | (sym >> sh_node);
@@ -553,11 +650,13 @@ __global__ void __launch_bounds__(kCmEncThreads, 1) cm_encode_chunked_kernel(con
                 const u32* pw = pbuf + (ch & 1) * (kCmEncChunk * 8);
                 const uint4* pv = reinterpret_cast<const uint4*>(pw);
                 const u8* sb = sbytes + (ch % 3) * kCmEncChunk;
+                if (MODE == 3) {
+                    rc_lane3(pw, sb, len, low, range, op, out);
+                }
                 uint4 a = pv[0], b = pv[1];
                 u32 sym = sb[0];
                 u32 x = mulhi_pinned(range, a.x);
-                u64 w3 = (MODE == 3) ? cm_mul_wide(range, a.x) : 0ull;   // MODE 3: product of the first decision
-                for (s32 k = 0; k < len; k++) {
+                for (s32 k = 0; MODE != 3 && k < len; k++) {
                     const uint4 ca = a, cb = b;
                     const u32 cs = sym;
                     const s32 kn = (k + 1 < len) ? k + 1 : k;  // the last byte re-reads itself; that product is unused
@@ -574,9 +673,7 @@ __global__ void __launch_bounds__(kCmEncThreads, 1) cm_encode_chunked_kernel(con
                         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym) : "r"(sp));
 #endif
                     }
-                    if (MODE == 3) {
-                        rc_byte3(low, range, w3, op, cs, ca, cb, a.x, pw + 8 * k, out);
-                    } else if (MODE == 2) {
+                    if (MODE == 2) {
 #ifdef BZ_CM_PROFILE
                         rc_byte2(low, range, op, cs, ca, cb, out, _ex);
 #else
