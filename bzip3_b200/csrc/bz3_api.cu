@@ -265,6 +265,7 @@ cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, i
 //            3 all paths, first edition                          4 tree kernel, lane-parallel chain warp
 //            5 all paths, one multiply per level                 6 walker warps (walk of 5) + model threads of 0/4
 //            7 = 6 with the slim model-thread loop               8 = 7, walker warps stop after three levels
+//            9 = 8 with the branch-light, parity-unrolled model-thread loop
 // Defaults can be overridden per process with BZ3_B200_CM_ENC / BZ3_B200_CM_DEC (tuning, tests).
 constexpr int kCmEncDefault = 0;
 constexpr int kCmDecDefault = 0;
@@ -309,6 +310,8 @@ cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s
         cm_decode_walkers_kernel<1, 0><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else if (s->cm_dec == 8)
         cm_decode_walkers_kernel<1, 1><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+    else if (s->cm_dec == 9)
+        cm_decode_walkers_kernel<2, 1><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
     else
         cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
     BZ_NOTE_LAUNCH();

@@ -940,6 +940,168 @@ BZ_D void cm_dec_model_thread_slim(u16* cm_smem, u32* ptab, volatile u32* vbyte,
     }
 }
 
+// Third edition of the model thread (variant 9), written against the measured cost of a TAKEN branch (~20
+// cycles, as much as two dependent multiplies).  In the slim loop above a thread of an off-path warp runs into
+// five of them per byte on a speculation hit (skip the predict block, skip the outcome block, skip the extra
+// barriers, skip the learn stores, loop back-edge): ~250 cycles per byte, more than the walkers need.  Here
+//   * the loop is unrolled by the parity of the byte index (ptab / byte-slot offsets become immediates, the
+//     loop-carried register shuffles disappear, half a back-edge per byte),
+//   * the real prediction after a miss sits at the END of the step that missed (no "if (!have)" at the top),
+//   * the barrier protocol and the learn stores are predicated instead of branched over.
+#if defined(BZ_EMU)
+BZ_D void cm_bar_byte_ready_or0() {
+    if (!__syncthreads_or(0))
+        if (!__syncthreads_or(0)) __syncthreads();
+}
+BZ_D void cm_learn_stores(bool on, u16* q0, u32 a, u16* q1, u32 b, u16* cell, u32 lo, u32 hi) {
+    if (on) {
+        *q0 = (u16)a;
+        *q1 = (u16)b;
+        cell[0] = (u16)lo;
+        cell[1] = (u16)hi;
+    }
+}
+#else
+// "byte ready" of the walker kernel seen from a model thread: barrier-OR with a false vote; if no walker
+// published, take part in the exact-test barrier-OR; if still nobody, in the barrier after the serial redo.
+BZ_D void cm_bar_byte_ready_or0() {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pf, p1, p2;\n\t"
+        "setp.ne.u32 pf, 0, 0;\n\t"
+        "bar.red.or.pred p1, 0, pf;\n\t"
+        "mov.pred p2, p1;\n\t"
+        "@!p1 bar.red.or.pred p2, 0, pf;\n\t"
+        "@!p2 bar.sync 0;\n\t"
+        "}" ::: "memory");
+}
+BZ_D void cm_learn_stores(bool on, u16* q0, u32 a, u16* q1, u32 b, u16* cell, u32 lo, u32 hi) {
+    const u32 s0 = (u32)__cvta_generic_to_shared(q0), s1 = (u32)__cvta_generic_to_shared(q1);
+    const u32 s2 = (u32)__cvta_generic_to_shared(cell);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %0, 0;\n\t"
+        "@p st.shared.u16 [%1], %2;\n\t"
+        "@p st.shared.u16 [%3], %4;\n\t"
+        "@p st.shared.u16 [%5], %6;\n\t"
+        "@p st.shared.u16 [%5+2], %7;\n\t"
+        "}" ::"r"((u32)on), "r"(s0), "h"((u16)a), "r"(s1), "h"((u16)b), "r"(s2), "h"((u16)lo), "h"((u16)hi)
+        : "memory");
+}
+#endif
+
+struct CmModelState {
+    int prev1, prev2;
+    u32 run, a, b, d, lo, hi;
+    u16* q1;
+    u16* cell;
+};
+
+// real prediction of the next byte from the registers (after a miss, and for byte 0) into half H of ptab
+template <int LAYOUT, int H>
+BZ_D void cm_model_predict(CmModelState& M, u32* ptab, u16* rows, const int node) {
+    M.run = (M.prev1 == M.prev2) ? M.run + 1 : 0;
+    const int flag = M.run > 2;
+    const u32 p = ((M.a + M.b) * 7 + M.d + M.d) >> 4;
+    M.cell = rows + flag * 17 + (p >> 12);
+    M.lo = M.cell[0];
+    M.hi = M.cell[1];
+    const int sse = (int)M.lo + ((((int)M.hi - (int)M.lo) * (int)(p & 4095)) >> 12);
+    cm_ptab_put<LAYOUT>(ptab, H * 256 + node, (u32)(sse * 3 + (int)p) << 14);
+}
+
+template <int LAYOUT, int HALF>
+BZ_D void cm_model_step(CmModelState& M, u16* cm_smem, u32* ptab, volatile u32* vbyte, const bool last, const int node,
+                        const int sh, u16* q0, u16* c1col, u16* rows) {
+    // speculation: this byte == prev1
+    const u32 hyp = (u32)M.prev1;
+    const bool on_h = node != 0 && ((256u | hyp) >> sh) == (u32)node;
+    u32 a_s = M.a, b_s = M.b, nl = M.lo, nh = M.hi;   // counters as (this byte == hyp) would leave them
+    if (on_h) {
+        const u32 ones = ((hyp >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
+        a_s = cm_adapt_bf(M.a, ones, 2);
+        b_s = cm_adapt_bf(M.b, ones, 4);
+        nl = cm_adapt_bf(M.lo, ones, 6);
+        nh = cm_adapt_bf(M.hi, ones, 6);
+    }
+    const u32 run_s = M.run + 1u;   // run rule (src/libbz3.c:367-370) applied to (prev1, prev1)
+    const int flag_s = run_s > 2;
+    const u32 p_s = ((a_s + b_s) * 7 + b_s + b_s) >> 4;
+    u16* const cell_s = rows + flag_s * 17 + (p_s >> 12);
+    u32 lo_s = cell_s[0], hi_s = cell_s[1];
+    {   // the pending update of this byte is not in shared memory yet (predicated, no branch)
+        const bool same = on_h && cell_s == M.cell, up = on_h && cell_s == M.cell + 1, dn = on_h && cell_s + 1 == M.cell;
+        lo_s = same ? nl : (up ? nh : lo_s);
+        hi_s = same ? nh : (dn ? nl : hi_s);
+    }
+    {
+        const int sse = (int)lo_s + ((((int)hi_s - (int)lo_s) * (int)(p_s & 4095)) >> 12);
+        cm_ptab_put<LAYOUT>(ptab, (HALF ^ 1) * 256 + node, (u32)(sse * 3 + (int)p_s) << 14);
+    }
+    cm_bar_byte_ready_or0();
+    const u32 byte = vbyte[HALF];
+    if (__builtin_expect(byte != hyp, 0)) {   // uniform across the CTA
+        // miss: learn the byte that really came, then predict the next one for real
+        u32 na = M.a, nb = M.b;
+        if (node != 0 && ((256u | byte) >> sh) == (u32)node) {
+            const u32 ones = ((byte >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
+            na = cm_adapt_bf(M.a, ones, 2);
+            nb = cm_adapt_bf(M.b, ones, 4);
+            *q0 = (u16)na;
+            *M.q1 = (u16)nb;
+            M.cell[0] = (u16)cm_adapt_bf(M.lo, ones, 6);
+            M.cell[1] = (u16)cm_adapt_bf(M.hi, ones, 6);
+        }
+        M.a = na;
+        M.d = nb;                       // this byte's order-1 counter is the next byte's prev2 counter
+        M.prev2 = M.prev1;
+        M.prev1 = (int)byte;
+        M.q1 = c1col + M.prev1 * 256;
+        M.b = *M.q1;                    // after the store above in program order
+        if (!last) {
+            cm_model_predict<LAYOUT, HALF ^ 1>(M, ptab, rows, node);
+            __syncthreads();   // ptab ready
+        }
+        return;
+    }
+    cm_learn_stores(on_h, q0, a_s, M.q1, b_s, M.cell, nl, nh);
+    M.a = a_s;
+    M.b = b_s;
+    M.d = b_s;
+    M.lo = lo_s;
+    M.hi = hi_s;
+    M.cell = cell_s;
+    M.run = run_s;
+    M.prev2 = M.prev1;   // == byte
+}
+
+template <int LAYOUT>
+BZ_D void cm_dec_model_thread_slim2(u16* cm_smem, u32* ptab, volatile u32* vbyte, s32 n, const int node) {
+    const int sh = node ? 8 - (31 - __clz(node)) : 8;                 // (256|byte) >> sh == node <=> on the path
+    u16* const q0 = cm_smem + node;
+    u16* const c1col = cm_smem + kCmC0 + node;                        // + prev * 256
+    u16* const rows = cm_smem + kCmC0 + kCmC1 + (2 * node) * 17;      // + flag * 17 + cell
+    CmModelState M;
+    M.prev1 = 0;
+    M.prev2 = 0;
+    M.run = 0;
+    M.q1 = c1col;
+    M.a = *q0;
+    M.b = *M.q1;
+    M.d = M.b;
+    M.lo = 0;
+    M.hi = 0;
+    M.cell = rows;
+    if (n <= 0) return;
+    cm_model_predict<LAYOUT, 0>(M, ptab, rows, node);
+    __syncthreads();   // ptab of byte 0 ready
+    for (s32 i = 0; i < n; i += 2) {
+        cm_model_step<LAYOUT, 0>(M, cm_smem, ptab, vbyte, i + 1 >= n, node, sh, q0, c1col, rows);
+        if (i + 1 < n) cm_model_step<LAYOUT, 1>(M, cm_smem, ptab, vbyte, i + 2 >= n, node, sh, q0, c1col, rows);
+    }
+}
+
 // ---- tree-parallel decoder ---------------------------------------------------------------------
 // Decoding is one dependent chain: the next context depends on the bit just decoded.  What does not
 // depend on the bits of the current byte is the probability of every one of the 255 tree nodes (no node
@@ -1986,7 +2148,8 @@ __global__ void __launch_bounds__(kCmDecW6Threads, 1) cm_decode_walkers_kernel(c
     for (int k = tid; k < 2048; k += kCmDecW6Threads) scode[k] = (k < insize) ? in[k] : 0;
     if (tid >= 256) {
         __syncthreads();
-        if (SLIM) cm_dec_model_thread_slim<1, 1>(cm_smem, ptab, pub + 16, n, tid - 256);
+        if (SLIM == 2) cm_dec_model_thread_slim2<1>(cm_smem, ptab, pub + 16, n, tid - 256);
+        else if (SLIM == 1) cm_dec_model_thread_slim<1, 1>(cm_smem, ptab, pub + 16, n, tid - 256);
         else cm_dec_model_thread<1, 1>(cm_smem, ptab, pub + 16, n, tid - 256);
         return;
     }
@@ -2059,6 +2222,7 @@ inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY((cudaFuncSetAttribute(cm_decode_walkers_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes)));
     BZ_CUDA_TRY((cudaFuncSetAttribute(cm_decode_walkers_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes)));
     BZ_CUDA_TRY((cudaFuncSetAttribute(cm_decode_walkers_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes)));
+    BZ_CUDA_TRY((cudaFuncSetAttribute(cm_decode_walkers_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmDecW6SmemBytes)));
     return cudaSuccess;
 }
 #endif

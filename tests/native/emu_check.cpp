@@ -75,6 +75,10 @@ EXPORT int emu_cm_decode(int variant, const uint8_t* in, int32_t insize, uint8_t
             b.x = kCmDecW6Threads;
             emu::launch(g, b, kCmDecW6SmemBytes, [&] { cm_decode_walkers_kernel<1, 1>(in, insize, out, n); });
             break;
+        case 9:
+            b.x = kCmDecW6Threads;
+            emu::launch(g, b, kCmDecW6SmemBytes, [&] { cm_decode_walkers_kernel<2, 1>(in, insize, out, n); });
+            break;
         case 5:
             b.x = kCmDecP2Threads;
             emu::launch(g, b, kCmDecP2SmemBytes, [&] { cm_decode_paths2_kernel(in, insize, out, n); });

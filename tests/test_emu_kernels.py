@@ -77,7 +77,7 @@ CM_CASES = cm_inputs()
 CM_IDS = [c[0] for c in CM_CASES]
 
 ENC_VARIANTS = [0, 1, 2, 4, 6]
-DEC_VARIANTS = [0, 1, 3, 4, 5, 6, 7, 8]
+DEC_VARIANTS = [0, 1, 3, 4, 5, 6, 7, 8, 9]
 
 
 @pytest.mark.parametrize("variant", ENC_VARIANTS)

@@ -159,17 +159,20 @@ def test_stage_unbwt_on_garbage_matches_reference_semantics(st, O):
         assert bytes(got[:n]) == bytes(want[:n]), (t, n, k, idx, first_diff(got[:n], want[:n]))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7],
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9],
                          ids=["two_tier", "single", "exact_tier_only", "all_paths_decode", "one_mul_enc_lanes_dec",
-                              "paths2_decode", "resume_enc_walkers_dec", "walkers_slim_dec"])
+                              "paths2_decode", "resume_enc_walkers_dec", "walkers_slim_dec", "walkers_prune_dec",
+                              "walkers_branchlight_dec"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_stage_cm(st, O, name, data, variant):
     a = arr(data)
     n = len(a)
     if variant in (1, 2) and n > 120_000:
         pytest.skip("cross-check kernel variants kept to small inputs")
-    if variant in (6, 7) and not NEW_UNTIMED:
-        pytest.skip("CM variants 6 and 7 have not run on a GPU yet (set BZ3_B200_TEST_NEW=1)")
+    if variant >= 4 and not NEW_UNTIMED:
+        # 4 and 5 ran bit-exact on a B200 (profiles/r01_cm_variants_eval_1MiB.log), but their serial fall-back loop
+        # was rewritten afterwards; 6..9 have not run on hardware at all
+        pytest.skip("CM variants 4..9 in their current form have not run on a GPU yet (set BZ3_B200_TEST_NEW=1)")
     pad = np.zeros(n + 16, np.uint8)
     pad[:n] = a
     want = np.zeros(2 * n + 64, np.uint8)

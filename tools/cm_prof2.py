@@ -44,7 +44,7 @@ def main():
                 p = prof()
                 rec["enc_v%d" % v] = {"stage1_busy": p[13] / n, "stage2_busy": p[14] / n, "coder_busy": p[15] / n,
                                       "exact_tier_cycles": p[32] / n, "exact_tier_bytes_frac": p[33] / n}
-            for v in (0, 4, 5, 6, 7, 8):
+            for v in (0, 4, 5, 6, 7, 8, 9):
                 L.bz3_b200_set_variant(st.handle, CM + 200, v)
                 back = np.zeros(n + 8, np.uint8)
                 L.bz3_b200_stage_cm_decode(st.handle, enc.ctypes.data_as(u8p), r, back.ctypes.data_as(u8p), n)

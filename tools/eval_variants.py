@@ -28,7 +28,8 @@ ENC_VARIANTS = {0: "chunked, select+mul.hi coder lane (round-1 default)", 4: "ch
 DEC_VARIANTS = {0: "tree, serial chain warp (round-1 default)", 3: "all paths, first edition",
                 4: "tree, lane-parallel chain warp", 5: "all paths, one multiply per level",
                 6: "walker warps (all-paths walk) + model threads", 7: "walker warps + slim model threads",
-                8: "walker warps (stop after 3 levels when outside their eighth) + slim model threads"}
+                8: "walker warps (stop after 3 levels when outside their eighth) + slim model threads",
+                9: "as 8, branch-light parity-unrolled model threads"}
 
 
 def main():
@@ -69,7 +70,7 @@ def main():
             print("%s: ratio %.3f, oracle on one host core: enc %.1f MB/s, dec %.1f MB/s" % (
                 name, rw / n, n / cpu_enc / 1e6, n / cpu_dec / 1e6), flush=True)
         # known-good kernels first, so that a fault in a new one cannot hide the baseline
-        order = [("enc", 0), ("dec", 0), ("enc", 4), ("dec", 4), ("enc", 6), ("dec", 6), ("dec", 7), ("dec", 8), ("dec", 5)]
+        order = [("enc", 0), ("dec", 0), ("enc", 4), ("dec", 4), ("enc", 6), ("dec", 6), ("dec", 7), ("dec", 8), ("dec", 9), ("dec", 5)]
         for kind, v in order:
             for name, _ in sets:
                 bwt, want, rw, cut, dw = prep[name]
@@ -145,7 +146,7 @@ def main():
         blk = np.ascontiguousarray(sets[0][1][: min(n, 1 << 20)])
         enc_o, r_o, e_o = refs.oracle_encode_block(bytes(blk), max(n, 1 << 20))
         combos = {}
-        for ve, vd in ((4, 4), (6, 7), (6, 8)):
+        for ve, vd in ((4, 4), (6, 8), (6, 9)):
             L.bz3_b200_set_variant(st.handle, CM + 100, ve)
             L.bz3_b200_set_variant(st.handle, CM + 200, vd)
             buf = np.zeros(refs.bound(max(n, 1 << 20)) + 64, np.uint8)
