@@ -2115,6 +2115,15 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
             __syncthreads();
             S.code = pub[HALF * 8 + 3];
             S.ip = (s32)pub[HALF * 8 + 4];
+            // the stream position only moves here (shifts happen in the serial redo), so this is also the only
+            // place where the window can need a refill -- not a test on the common path
+            if (S.ip - S.wlo >= 1024) {   // uniform; visibility to the serial reader is ordered by the next barrier
+                for (int k = (int)v; k < 1024; k += 256) {
+                    const s32 src = S.wlo + 2048 + k;
+                    scode[src & 2047] = (src < insize) ? in[src] : 0;
+                }
+                S.wlo += 1024;
+            }
         }
         BZ_SPROF_AFTER_BAR(S, 3, pub + HALF * 8);
     }
@@ -2122,13 +2131,6 @@ BZ_D void cm_dec_walk_step(const CmWalkConsts& K, CmWalkState& S, const s32 i, u
     S.low = lds_u32<PB + 4>(pub_a);
     S.range = lds_u32<PB + 8>(pub_a);
     if (v == 0) out[i] = (u8)byte;
-    if (S.ip - S.wlo >= 1024) {   // uniform; visibility to the serial reader is ordered by the next barrier
-        for (int k = (int)v; k < 1024; k += 256) {
-            const s32 src = S.wlo + 2048 + k;
-            scode[src & 2047] = (src < insize) ? in[src] : 0;
-        }
-        S.wlo += 1024;
-    }
     S.have = byte == S.prevb;
     S.prevb = byte;
     BZ_SPROF(S, 4);
