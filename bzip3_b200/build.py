@@ -39,5 +39,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_tools() -> None:
+    """Extras for tuning sessions (git-ignored outputs under tools/variants/): the library with the clock64
+    phase counters compiled in (-DBZ_CM_PROFILE, read by tools/cm_prof2.py) and the latency micro-benchmarks."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "tools", "variants")
+    os.makedirs(out, exist_ok=True)
+    for cmd in ([NVCC] + FLAGS + ["-DBZ_CM_PROFILE", "-o", os.path.join(out, "lib_cmprof.so"), os.path.join(CSRC, "bz3_api.cu")],
+                [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", os.path.join(out, "ubench"),
+                 os.path.join(root, "tools", "ubench.cu")]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed: " + " ".join(cmd[-3:]))
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--tools" in sys.argv:
+        build_tools()
+        print("built tools/variants/lib_cmprof.so and tools/variants/ubench")
