@@ -535,8 +535,7 @@ __global__ void __launch_bounds__(kLzpBulkThreads) lzp_decode_bulk_kernel(const 
                 s_tail = nt;
             }
         }
-        __threadfence();
-        __syncthreads();
+        __syncthreads();   // orders the global writes above for every thread of the block (reads below bypass L1)
         if (nlit > 0) tail = s_tail;
         op += nlit;
         ip += nlit;
@@ -588,7 +587,6 @@ __global__ void __launch_bounds__(kLzpBulkThreads) lzp_decode_bulk_kernel(const 
         } else if (count > 0) {
             const s32 dist = op - ref;  // > 0; the source [ref, op) is final, the copy repeats it with period dist
             for (s32 k = t; k < count; k += kLzpBulkThreads) out[op + k] = __ldcg(out + ref + (dist >= count ? k : k % dist));
-            __threadfence();
             __syncthreads();
             op += count;
             tail = (u32)__ldcg(out + op - 1) | ((u32)__ldcg(out + op - 2) << 8) | ((u32)__ldcg(out + op - 3) << 16) |
