@@ -588,21 +588,38 @@ __global__ void __launch_bounds__(kCmEncThreads, 1) cm_encode_chunked_kernel(con
                 __syncwarp();
                 if (lane < 8) {
                     u16* pm = pmid + (it & 1) * (kCmEncChunk * 8) + lane;
-                    int symn = sb[0];   // MODE 3: the next symbol is read one byte ahead (its load cannot pass the stores below)
-#pragma unroll(MODE == 3 ? 2 : 1)
-                    for (s32 k = 0; k < len; k++) {
-                        const int sym = (MODE == 3) ? symn : (int)sb[k];
-                        if (MODE == 3) symn = sb[(k + 1 < len) ? k + 1 : k];
-                        const int node = top | (sym >> sh_node);
-                        const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
-                        u16* q0 = c0 + node;
-                        u16* q1 = c1 + prev1 * 256 + node;
-                        const int a = *q0, b = *q1, d = c1[prev2 * 256 + node];
-                        pm[k * 8] = (u16)(((a + b) * 7 + d + d) >> 4);
-                        *q0 = (u16)cm_adapt_bf((u32)a, ones, 2);
-                        *q1 = (u16)cm_adapt_bf((u32)b, ones, 4);
-                        prev2 = prev1;
-                        prev1 = sym;
+                    if (MODE == 3) {
+                        // the next symbol is read one byte ahead (its load cannot pass the stores below); two bytes per trip
+                        int symn = sb[0];
+#pragma unroll 2
+                        for (s32 k = 0; k < len; k++) {
+                            const int sym = symn;
+                            symn = sb[(k + 1 < len) ? k + 1 : k];
+                            const int node = top | (sym >> sh_node);
+                            const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
+                            u16* q0 = c0 + node;
+                            u16* q1 = c1 + prev1 * 256 + node;
+                            const int a = *q0, b = *q1, d = c1[prev2 * 256 + node];
+                            pm[k * 8] = (u16)(((a + b) * 7 + d + d) >> 4);
+                            *q0 = (u16)cm_adapt_bf((u32)a, ones, 2);
+                            *q1 = (u16)cm_adapt_bf((u32)b, ones, 4);
+                            prev2 = prev1;
+                            prev1 = sym;
+                        }
+                    } else {
+                        for (s32 k = 0; k < len; k++) {
+                            const int sym = sb[k];
+                            const int node = top | (sym >> sh_node);
+                            const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
+                            u16* q0 = c0 + node;
+                            u16* q1 = c1 + prev1 * 256 + node;
+                            const int a = *q0, b = *q1, d = c1[prev2 * 256 + node];
+                            pm[k * 8] = (u16)(((a + b) * 7 + d + d) >> 4);
+                            *q0 = (u16)cm_adapt_bf((u32)a, ones, 2);
+                            *q1 = (u16)cm_adapt_bf((u32)b, ones, 4);
+                            prev2 = prev1;
+                            prev1 = sym;
+                        }
                     }
                 }
             }
@@ -614,32 +631,52 @@ __global__ void __launch_bounds__(kCmEncThreads, 1) cm_encode_chunked_kernel(con
                 const u8* sb = sbytes + (ch % 3) * kCmEncChunk;
                 const u16* pm = pmid + (ch & 1) * (kCmEncChunk * 8) + lane;
                 u32* pb = pbuf + (ch & 1) * (kCmEncChunk * 8) + lane;
-                int symn = sb[0], pn = pm[0];   // MODE 3: symbol and mixed probability are read one byte ahead
-#pragma unroll(MODE == 3 ? 2 : 1)
-                for (s32 k = 0; k < len; k++) {
-                    const int sym = (MODE == 3) ? symn : (int)sb[k];
-                    const int p = (MODE == 3) ? pn : (int)pm[k * 8];
-                    if (MODE == 3) {
-                        const s32 kn = (k + 1 < len) ? k + 1 : k;
-                        symn = sb[kn];
-                        pn = pm[kn * 8];
-                    }
-                    run = (prev1 == prev2) ? run + 1 : 0;           // run flag of this byte (src/libbz3.c:367-372)
-                    const int flag = run > 2;
-                    const int node = top | (sym >> sh_node);
-                    const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
-                    u16* cell = c2 + (2 * node + flag) * 17 + (p >> 12);
-                    const int lo = cell[0], hi = cell[1];
-                    const int sse = lo + (((hi - lo) * (p & 4095)) >> 12);
-                    {
+                if (MODE == 3) {
+                    // symbol and mixed probability are read one byte ahead; two bytes per trip
+                    int symn = sb[0], pn = pm[0];
+#pragma unroll 2
+                    for (s32 k = 0; k < len; k++) {
+                        const int sym = symn, p = pn;
+                        {
+                            const s32 kn = (k + 1 < len) ? k + 1 : k;
+                            symn = sb[kn];
+                            pn = pm[kn * 8];
+                        }
+                        run = (prev1 == prev2) ? run + 1 : 0;           // run flag of this byte (src/libbz3.c:367-372)
+                        const int flag = run > 2;
+                        const int node = top | (sym >> sh_node);
+                        const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
+                        u16* cell = c2 + (2 * node + flag) * 17 + (p >> 12);
+                        const int lo = cell[0], hi = cell[1];
+                        const int sse = lo + (((hi - lo) * (p & 4095)) >> 12);
                         const u32 m = (u32)(sse * 3 + p) << 14;
-                        // MODE 2: the coder lane multiplies by M for a 1-bit and by -M for a 0-bit (see rc_fast_byte2)
-                        pb[k * 8] = (MODE >= 2 && !ones) ? 0u - m : m;
+                        pb[k * 8] = ones ? m : 0u - m;   // the coder lane multiplies by M for a 1-bit and by -M for a 0-bit
+                        cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
+                        cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
+                        prev2 = prev1;
+                        prev1 = sym;
                     }
-                    cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
-                    cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
-                    prev2 = prev1;
-                    prev1 = sym;
+                } else {
+                    for (s32 k = 0; k < len; k++) {
+                        const int sym = sb[k];
+                        const int p = pm[k * 8];
+                        run = (prev1 == prev2) ? run + 1 : 0;           // run flag of this byte (src/libbz3.c:367-372)
+                        const int flag = run > 2;
+                        const int node = top | (sym >> sh_node);
+                        const u32 ones = ((sym >> sh_bit) & 1) ? 0xFFFFu : 0u;
+                        u16* cell = c2 + (2 * node + flag) * 17 + (p >> 12);
+                        const int lo = cell[0], hi = cell[1];
+                        const int sse = lo + (((hi - lo) * (p & 4095)) >> 12);
+                        {
+                            const u32 m = (u32)(sse * 3 + p) << 14;
+                            // MODE 2: the coder lane multiplies by M for a 1-bit and by -M for a 0-bit (see rc_byte2)
+                            pb[k * 8] = (MODE == 2 && !ones) ? 0u - m : m;
+                        }
+                        cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
+                        cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
+                        prev2 = prev1;
+                        prev1 = sym;
+                    }
                 }
             }
         } else if (warp == 1) {
