@@ -12,6 +12,9 @@
 // dynamic shared memory of a kernel, and a hint inside spin-waits (both have a CPU-emulator meaning, below)
 #define BZ_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #define BZ_SPIN_HINT()
+// kernel launch: BZ_LAUNCH(grid, block, smem, stream, kernel<...>)(args...).  The kernel name comes last so that
+// template argument lists may contain commas.  (The CPU emulator of the tests has its own definition.)
+#define BZ_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
 #else
 #define BZ_HD inline
 #define BZ_D inline

@@ -53,7 +53,7 @@ BZ_HD u32 crc_xpow_bytes(const u32* xpow8, u64 nbytes) {
     return p;
 }
 
-#if defined(__CUDACC__)
+#if defined(BZ_DEVICE_CODE)
 __constant__ CrcTables c_crc;
 
 constexpr int kCrcChunk = 2048;   // bytes per thread
@@ -109,7 +109,7 @@ inline cudaError_t crc_launch(cudaStream_t st, const u8* buf, u32 n, u32 init, u
     u32 chunks = (n + kCrcChunk - 1) / kCrcChunk;
     u32 blocks = (chunks + kCrcThreads - 1) / kCrcThreads;
     if (blocks == 0) blocks = 1;  // n == 0: only the init term
-    crc_kernel<<<blocks, kCrcThreads, 0, st>>>(buf, n, init, acc); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(blocks, kCrcThreads, 0, st, crc_kernel)(buf, n, init, acc); BZ_NOTE_LAUNCH();
     return cudaGetLastError();
 }
 #endif

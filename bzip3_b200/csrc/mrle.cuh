@@ -111,10 +111,10 @@ inline cudaError_t mrle_encode(cudaStream_t st, const u8* in, u32 n, u8* out, co
         BZ_CUDA_TRY(cudaMemcpyAsync(S.heads + nruns, &n, sizeof(u32), cudaMemcpyHostToDevice, st));
         u32 blocks = (nruns + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        mrle_gain_kernel<<<blocks, 256, 0, st>>>(in, S.heads, nruns, S.gain); BZ_NOTE_LAUNCH();
+        BZ_LAUNCH(blocks, 256, 0, st, mrle_gain_kernel)(in, S.heads, nruns, S.gain); BZ_NOTE_LAUNCH();
         BZ_CUDA_TRY(cudaGetLastError());
     }
-    mrle_bitmap_kernel<<<1, 256, 0, st>>>(S.gain, out, S.flagged); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(1, 256, 0, st, mrle_bitmap_kernel)(S.gain, out, S.flagged); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     u32 total = 0;
     if (nruns > 0) {
@@ -245,7 +245,7 @@ inline cudaError_t mrle_decode(cudaStream_t st, const u8* in, u32 maxin, u8* out
     if (maxin < 32) { *err = 1; return cudaSuccess; }  // :310
     const u32 m = maxin - 32;
     const u8* body = in + 32;
-    mrle_unpack_bitmap_kernel<<<1, 256, 0, st>>>(in, S.flagged); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(1, 256, 0, st, mrle_unpack_bitmap_kernel)(in, S.flagged); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     u32* d_final_map = S.d_count;                                              // [0]
     ExpandElem* d_total = reinterpret_cast<ExpandElem*>(S.d_count + 1);       // [1..3]
@@ -260,7 +260,7 @@ inline cudaError_t mrle_decode(cudaStream_t st, const u8* in, u32 maxin, u8* out
     BZ_CUDA_TRY(cudaMemcpyAsync(S.h_count, S.d_count, sizeof(u32), cudaMemcpyDeviceToHost, st));
     BZ_CUDA_TRY(cudaStreamSynchronize(st));
     u32 final_state = S.h_count[0] & 1u;  // image of state 0 under the whole stream
-    mrle_tail_fix_kernel<<<1, 1, 0, st>>>(body, m, final_state, d_total, out, outlen, d_produced); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(1, 1, 0, st, mrle_tail_fix_kernel)(body, m, final_state, d_total, out, outlen, d_produced); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(S.h_count, d_produced, sizeof(u32), cudaMemcpyDeviceToHost, st));
     BZ_CUDA_TRY(cudaStreamSynchronize(st));

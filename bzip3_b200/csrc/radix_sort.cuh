@@ -86,7 +86,7 @@ rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, 
                   int shift, u32 mask, const u32* __restrict__ bases, u32 ntiles) {
     constexpr int ITEMS = RsCfg<K>::kItems;
     constexpr u32 TILE = kRsThreads * ITEMS;
-    extern __shared__ __align__(16) unsigned char rs_smem[];
+    BZ_DYN_SMEM(unsigned char, rs_smem);
     u32* warp_cnt = reinterpret_cast<u32*>(rs_smem);              // [kRsWarps][256]
     u32* lbase = warp_cnt + kRsWarps * 256;                       // [256] first sorted slot of digit in tile
     u32* gdelta = lbase + 256;                                    // [256] global index minus tile slot
@@ -260,17 +260,17 @@ cudaError_t rs_pass(cudaStream_t st, const K* kin, ValGen vgen, K* kout, u32* vo
     const u32 ntiles = rs_num_tiles<K>(n);
     const u32 mask = (1u << bits) - 1u;
     u32* hist = temp;
-    rs_tile_hist_kernel<K><<<ntiles, kRsThreads, 0, st>>>(kin, n, shift, mask, hist, ntiles); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(ntiles, kRsThreads, 0, st, rs_tile_hist_kernel<K>)(kin, n, shift, mask, hist, ntiles); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     const u32 hn = 256 * ntiles;
-    rs_row_total_kernel<<<256, 256, 0, st>>>(hist, ntiles, hist + hn); BZ_NOTE_LAUNCH();
-    rs_row_scan_kernel<<<256, 256, 0, st>>>(hist, ntiles, hist + hn); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(256, 256, 0, st, rs_row_total_kernel)(hist, ntiles, hist + hn); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(256, 256, 0, st, rs_row_scan_kernel)(hist, ntiles, hist + hn); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     auto kern = rs_scatter_kernel<K, KOUT, VOUT, ValGen>;
     const size_t smem = rs_scatter_smem<K>();
     // set every time: the attribute is per device and a process may drive several GPUs
     BZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ntiles, kRsThreads, smem, st>>>(kin, vgen, kout, vout, n, shift, mask, hist, ntiles); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(ntiles, kRsThreads, smem, st, kern)(kin, vgen, kout, vout, n, shift, mask, hist, ntiles); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     return cudaSuccess;
 }

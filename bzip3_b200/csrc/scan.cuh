@@ -126,16 +126,16 @@ cudaError_t device_scan(cudaStream_t st, In in, Out out, u32 n, T identity, Op o
     }
     const u32 tiles = scan_num_tiles(n);
     T* sums = temp;
-    scan_reduce_kernel<T, Op, In><<<tiles, kScanThreads, 0, st>>>(in, n, sums, identity, op); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(tiles, kScanThreads, 0, st, scan_reduce_kernel<T, Op, In>)(in, n, sums, identity, op); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     if (tiles > 1) {
         // exclusive scan of the tile sums in place; its grand total lands in sums[tiles]
         BZ_CUDA_TRY((device_scan<T, Op, PtrIn<T>, PtrOutExcl<T>>(st, PtrIn<T>{sums}, PtrOutExcl<T>{sums}, tiles, identity,
                                                                  op, temp + tiles + 1, total_out)));
-        scan_down_kernel<T, Op, In, Out><<<tiles, kScanThreads, 0, st>>>(in, out, n, sums, identity, op); BZ_NOTE_LAUNCH();
+        BZ_LAUNCH(tiles, kScanThreads, 0, st, scan_down_kernel<T, Op, In, Out>)(in, out, n, sums, identity, op); BZ_NOTE_LAUNCH();
     } else {
         if (total_out) BZ_CUDA_TRY(cudaMemcpyAsync(total_out, sums, sizeof(T), cudaMemcpyDeviceToDevice, st));
-        scan_down_kernel<T, Op, In, Out><<<1, kScanThreads, 0, st>>>(in, out, n, (const T*)nullptr, identity, op); BZ_NOTE_LAUNCH();
+        BZ_LAUNCH(1, kScanThreads, 0, st, scan_down_kernel<T, Op, In, Out>)(in, out, n, (const T*)nullptr, identity, op); BZ_NOTE_LAUNCH();
     }
     BZ_CUDA_TRY(cudaGetLastError());
     return cudaSuccess;

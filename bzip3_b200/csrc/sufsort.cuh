@@ -142,7 +142,7 @@ inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const 
     }
     const int TPB = 256;
     BZ_CUDA_TRY(cudaMemsetAsync(B.isa + n, 0, sizeof(u32), st));
-    sa_init_keys_kernel<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(T, n, B.key[0]); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH((n + TPB - 1) / TPB, TPB, 0, st, sa_init_keys_kernel)(T, n, B.key[0]); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     bool in_b = false;
     int nev = 0;
@@ -173,7 +173,7 @@ inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const 
         if (h >= n) return cudaErrorUnknown;  // cannot happen: every suffix is unique within n symbols
         rounds++;
         record_passes += (u64)m * (u64)((2 * rank_bits + 7) / 8);
-        sa_build_keys_kernel<<<(m + TPB - 1) / TPB, TPB, 0, st>>>(B.val[vc], B.grp[lc], B.isa, m, (u32)h, rank_bits,
+        BZ_LAUNCH((m + TPB - 1) / TPB, TPB, 0, st, sa_build_keys_kernel)(B.val[vc], B.grp[lc], B.isa, m, (u32)h, rank_bits,
                                                                   B.key[0]); BZ_NOTE_LAUNCH();
         BZ_CUDA_TRY(cudaGetLastError());
         // sort (key[0], val[vc]) <-> (key[1], val[vc^1])
@@ -199,7 +199,7 @@ inline cudaError_t suffix_bwt(cudaStream_t st, const u8* T, u32 n, u8* U, const 
     BZ_CUDA_TRY(cudaMemcpyAsync(B.h_count, B.isa, sizeof(u32), cudaMemcpyDeviceToHost, st));
     BZ_CUDA_TRY(cudaStreamSynchronize(st));
     u32 idx = B.h_count[0];
-    bwt_gather_kernel<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(T, B.sa, n, idx, U); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH((n + TPB - 1) / TPB, TPB, 0, st, bwt_gather_kernel)(T, B.sa, n, idx, U); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     *idx_out = (s32)idx;
     return cudaSuccess;

@@ -189,8 +189,8 @@ inline cudaError_t unbwt(cudaStream_t st, const u8* L, u32 n, s32 idx, u8* out, 
     BZ_CUDA_TRY(cudaMemsetAsync(B.hist, 0, 256 * sizeof(u32), st));
     u32 hb = (n + 256 * 64 - 1) / (256 * 64);
     if (hb > 148 * 8) hb = 148 * 8;
-    hist256_kernel<<<hb, 256, 0, st>>>(L, n, B.hist); BZ_NOTE_LAUNCH();
-    unbwt_starts_kernel<<<1, 256, 0, st>>>(B.hist, B.start); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(hb, 256, 0, st, hist256_kernel)(L, n, B.hist); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(1, 256, 0, st, unbwt_starts_kernel)(B.hist, B.start); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemsetAsync(B.psi, 0, sizeof(u32), st));
     BZ_CUDA_TRY((rs_pass<u8, false, true, ValRowOfL>(st, L, ValRowOfL{(u32)idx}, (u8*)nullptr, B.psi + 1, n, 0, 8, B.temp)));
@@ -198,17 +198,17 @@ inline cudaError_t unbwt(cudaStream_t st, const u8* L, u32 n, s32 idx, u8* out, 
     u32 K;
     unbwt_geometry(n, &lg, &K);
     const u32 cnt = K + 1;
-    unbwt_walk1_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(B.psi, K, (1u << lg) - 1u, lg, (u32)idx, B.nxt[0], B.len); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH((cnt + 255) / 256, 256, 0, st, unbwt_walk1_kernel)(B.psi, K, (1u << lg) - 1u, lg, (u32)idx, B.nxt[0], B.len); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(B.dist[0], B.len, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, st));
     int cur = 0;
     for (u32 span = 1; span < cnt; span <<= 1) {
-        unbwt_jump_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(B.nxt[cur], B.dist[cur], cnt, B.nxt[cur ^ 1], B.dist[cur ^ 1]); BZ_NOTE_LAUNCH();
+        BZ_LAUNCH((cnt + 255) / 256, 256, 0, st, unbwt_jump_kernel)(B.nxt[cur], B.dist[cur], cnt, B.nxt[cur ^ 1], B.dist[cur ^ 1]); BZ_NOTE_LAUNCH();
         cur ^= 1;
     }
     BZ_CUDA_TRY(cudaGetLastError());
     const u32 limit = 2 * (n >> 1);
-    unbwt_walk2_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(B.psi, B.start, K, lg, (u32)idx, B.nxt[cur], B.dist[cur], B.len,
+    BZ_LAUNCH((cnt + 255) / 256, 256, 0, st, unbwt_walk2_kernel)(B.psi, B.start, K, lg, (u32)idx, B.nxt[cur], B.dist[cur], B.len,
                                                           limit, out); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     // path length: n for a valid transform
@@ -221,12 +221,12 @@ inline cudaError_t unbwt(cudaStream_t st, const u8* L, u32 n, s32 idx, u8* out, 
         const u32 lastc = *reinterpret_cast<const u8*>(B.h_count + 300);
         const u32 qstar = B.h_count[1 + lastc];
         BZ_CUDA_TRY(cudaMemsetAsync(B.big, 0, 65536 * sizeof(u32), st));
-        unbwt_bigram_kernel<<<148 * 4, 256, 0, st>>>(B.psi, B.start, n, qstar, B.big); BZ_NOTE_LAUNCH();
-        unbwt_filler_words_kernel<<<1, 1, 0, st>>>(B.big, n, lastc, qstar, B.d_count); BZ_NOTE_LAUNCH();
-        unbwt_fill_kernel<<<((n >> 1) + 255) / 256, 256, 0, st>>>(out, n, m, B.d_count); BZ_NOTE_LAUNCH();
+        BZ_LAUNCH(148 * 4, 256, 0, st, unbwt_bigram_kernel)(B.psi, B.start, n, qstar, B.big); BZ_NOTE_LAUNCH();
+        BZ_LAUNCH(1, 1, 0, st, unbwt_filler_words_kernel)(B.big, n, lastc, qstar, B.d_count); BZ_NOTE_LAUNCH();
+        BZ_LAUNCH(((n >> 1) + 255) / 256, 256, 0, st, unbwt_fill_kernel)(out, n, m, B.d_count); BZ_NOTE_LAUNCH();
         BZ_CUDA_TRY(cudaGetLastError());
     }
-    unbwt_last_byte_kernel<<<1, 1, 0, st>>>(L, out, n); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(1, 1, 0, st, unbwt_last_byte_kernel)(L, out, n); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     return cudaSuccess;
 }

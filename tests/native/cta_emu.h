@@ -367,6 +367,63 @@ inline long long clock64() { return (long long)::emu::g_cta->switches; }
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> inline T max(T a, T b) { return a > b ? a : b; }
 
+// ---- the slice of the CUDA runtime that the host-side launch sequences in bzip3_b200/csrc/*.cuh use -------------
+// "Device" memory is host memory here, a stream is synchronous, a launch runs the grid to completion.
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+constexpr cudaError_t cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorUnknown = 999;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) {
+    memmove(d, s, n);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) {
+    memset(d, v, n);
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+inline const char* cudaGetErrorName(cudaError_t) { return "emu"; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+template <class T>
+inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* src, size_t n) {
+    memcpy(&sym, src, n);
+    return cudaSuccess;
+}
+template <class F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+#define __constant__ static
+
+namespace emu {
+// BZ_LAUNCH(grid, block, smem, stream, kernel)(args...)
+template <class K>
+struct Launcher {
+    unsigned grid, block;
+    size_t smem;
+    K kern;
+    template <class... A>
+    void operator()(A&&... a) {
+        Dim3 g, b;
+        g.x = grid;
+        b.x = block;
+        launch(g, b, smem, [&] { kern(a...); });
+    }
+};
+template <class K>
+inline Launcher<K> make_launcher(unsigned grid, unsigned block, size_t smem, K k) { return Launcher<K>{grid, block, smem, k}; }
+}  // namespace emu
+#define BZ_LAUNCH(grid, block, smem, stream, ...) \
+    ::emu::make_launcher((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&](auto&&... _a) { __VA_ARGS__(_a...); })
+#define BZ_CUDA_TRY(expr)                  \
+    do {                                   \
+        cudaError_t _e = (expr);           \
+        if (_e != cudaSuccess) return _e;  \
+    } while (0)
+#define BZ_NOTE_LAUNCH() ((void)0)
+
 // dynamic shared memory: kernels declare it with BZ_DYN_SMEM(type, name)
 #define BZ_DYN_SMEM(type, name) type* const name = reinterpret_cast<type*>(::emu::g_dyn_smem)
 // a spin-wait on shared/global memory must give the other fibers a chance to run
