@@ -186,11 +186,11 @@ cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* 
     if (n < kLzpMinMatch + 32) { *result = -1; return cudaSuccess; }
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
     if (s->variant[BZ3_STAGE_LZP] == 1)
-        lzp_encode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+        BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_serial_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else if (s->variant[BZ3_STAGE_LZP] == 2)   // several windows in flight (opt-in until timed on the GPU)
-        lzp_encode_warp_pf_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+        BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_pf_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else
-        lzp_encode_warp_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+        BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -203,11 +203,11 @@ cudaError_t run_lzp_decode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32 m
     if (n < 4) { *result = -1; return cudaSuccess; }
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
     if (s->variant[BZ3_STAGE_LZP] == 1)
-        lzp_decode_serial_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+        BZ_LAUNCH(1, 32, 0, s->stream, lzp_decode_serial_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else if (s->variant[BZ3_STAGE_LZP] == 2)   // bulk decoder (opt-in until timed on the GPU)
-        lzp_decode_bulk_kernel<<<1, kLzpBulkThreads, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+        BZ_LAUNCH(1, kLzpBulkThreads, 0, s->stream, lzp_decode_bulk_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else
-        lzp_decode_warp_kernel<<<1, 32, 0, s->stream>>>(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+        BZ_LAUNCH(1, 32, 0, s->stream, lzp_decode_warp_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -278,15 +278,15 @@ int env_int(const char* name, int fallback) {
 cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* out_size) {
     s32* d_res = reinterpret_cast<s32*>(s->d_scal + 12);
     if (s->cm_enc == 1)
-        cm_encode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+        BZ_LAUNCH(1, kCmThreads, kCmSmemBytes, s->stream, cm_encode_single_kernel)(d_in, n, d_out, d_res);
     else if (s->cm_enc == 2)
-        cm_encode_chunked_kernel<1><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+        BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<1>)(d_in, n, d_out, d_res);
     else if (s->cm_enc == 4)
-        cm_encode_chunked_kernel<2><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+        BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<2>)(d_in, n, d_out, d_res);
     else if (s->cm_enc == 6)
-        cm_encode_chunked_kernel<3><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+        BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<3>)(d_in, n, d_out, d_res);
     else
-        cm_encode_chunked_kernel<0><<<1, kCmEncThreads, kCmEncSmemBytes, s->stream>>>(d_in, n, d_out, d_res);
+        BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<0>)(d_in, n, d_out, d_res);
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 12, d_res, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -297,23 +297,23 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
 
 cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s32 n) {
     if (s->cm_dec == 1)
-        cm_decode_single_kernel<<<1, kCmThreads, kCmSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmThreads, kCmSmemBytes, s->stream, cm_decode_single_kernel)(d_in, insize, d_out, n);
     else if (s->cm_dec == 3)
-        cm_decode_paths_kernel<<<1, kCmDecPathsThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmDecPathsThreads, kCmDecSmemBytes, s->stream, cm_decode_paths_kernel)(d_in, insize, d_out, n);
     else if (s->cm_dec == 4)
-        cm_decode_lanes_kernel<<<1, kCmDecThreads, kCmDecLanesSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmDecThreads, kCmDecLanesSmemBytes, s->stream, cm_decode_lanes_kernel)(d_in, insize, d_out, n);
     else if (s->cm_dec == 5)
-        cm_decode_paths2_kernel<<<1, kCmDecP2Threads, kCmDecP2SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmDecP2Threads, kCmDecP2SmemBytes, s->stream, cm_decode_paths2_kernel)(d_in, insize, d_out, n);
     else if (s->cm_dec == 6)
-        cm_decode_walkers_kernel<0, 0><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<0, 0>)(d_in, insize, d_out, n);
     else if (s->cm_dec == 7)
-        cm_decode_walkers_kernel<1, 0><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<1, 0>)(d_in, insize, d_out, n);
     else if (s->cm_dec == 8)
-        cm_decode_walkers_kernel<1, 1><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<1, 1>)(d_in, insize, d_out, n);
     else if (s->cm_dec == 9)
-        cm_decode_walkers_kernel<2, 1><<<1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<2, 1>)(d_in, insize, d_out, n);
     else
-        cm_decode_tree_kernel<<<1, kCmDecThreads, kCmDecSmemBytes, s->stream>>>(d_in, insize, d_out, n);
+        BZ_LAUNCH(1, kCmDecThreads, kCmDecSmemBytes, s->stream, cm_decode_tree_kernel)(d_in, insize, d_out, n);
     BZ_NOTE_LAUNCH();
     return cudaGetLastError();
 }

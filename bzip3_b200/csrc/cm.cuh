@@ -2246,7 +2246,7 @@ __global__ void __launch_bounds__(kCmDecW6Threads, 1) cm_decode_walkers_kernel(c
 #endif
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(BZ_EMU)
 inline cudaError_t cm_set_smem_attrs() {
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_encode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));
     BZ_CUDA_TRY(cudaFuncSetAttribute(cm_decode_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmSmemBytes));

@@ -55,14 +55,16 @@ BZ_HD size_t block_bound(size_t n) { return n + n / 50 + 32; }  // src/libbz3.c:
             return _e;                                                                            \
         }                                                                                         \
     } while (0)
+#endif  // __CUDACC__
 
+#if defined(BZ_DEVICE_CODE)
 // every kernel launch of the library is counted per host thread (bench.py reports it as gpu_launches)
 inline u64& launch_counter() {
     static thread_local u64 c = 0;
     return c;
 }
 #define BZ_NOTE_LAUNCH() (++::bz3::launch_counter())
-#endif  // __CUDACC__
+#endif
 
 #if defined(BZ_DEVICE_CODE)
 

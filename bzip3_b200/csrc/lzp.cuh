@@ -132,7 +132,7 @@ BZ_HD s32 lzp_decode_serial(const u8* in, s32 n, u8* out, s32 max, s32* lut) {
     return op;
 }
 
-#if defined(__CUDACC__)
+#if defined(BZ_DEVICE_CODE)
 __global__ void lzp_encode_serial_kernel(const u8* in, s32 n, u8* out, s32* lut, s32* result) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *result = lzp_encode_serial(in, n, out, lut);
 }

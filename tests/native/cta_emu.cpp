@@ -2,6 +2,8 @@
 // Test infrastructure only.
 #include "cta_emu.h"
 
+#include <mutex>
+
 namespace emu {
 Cta* g_cta = nullptr;
 Fiber* g_cur = nullptr;
@@ -52,7 +54,10 @@ static char* get_stack(size_t i) {
 static unsigned char* g_smem_buf = nullptr;
 static size_t g_smem_cap = 0;
 
+static std::mutex g_launch_mutex;   // one grid at a time: the emulator state and the kernels' static "shared" arrays are global
+
 void launch(Dim3 grid, Dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
     const unsigned nthreads = block.x * block.y * block.z;
     if (nthreads == 0 || nthreads > (unsigned)kMaxThreads) { fprintf(stderr, "[cta_emu] bad block size\n"); abort(); }
     if (dyn_smem_bytes + 64 > g_smem_cap) {

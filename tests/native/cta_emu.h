@@ -395,6 +395,35 @@ inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* src, size_t n) {
 }
 template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+// memory, devices, streams, events: one "device", everything synchronous
+constexpr unsigned cudaStreamNonBlocking = 1;
+template <class T>
+inline cudaError_t cudaMalloc(T** p, size_t n) {
+    *p = static_cast<T*>(aligned_alloc(256, (n + 255) & ~(size_t)255));
+    if (*p) memset(*p, 0xCD, n);   // device memory is not zeroed
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+template <class T>
+inline cudaError_t cudaMallocHost(T** p, size_t n) {
+    *p = static_cast<T*>(aligned_alloc(256, (n + 255) & ~(size_t)255));
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+template <class T>
+inline cudaError_t cudaMemcpyFromSymbol(void* dst, const T& sym, size_t n) {
+    memcpy(dst, &sym, n);
+    return cudaSuccess;
+}
 #define __constant__ static
 
 namespace emu {
@@ -422,7 +451,6 @@ inline Launcher<K> make_launcher(unsigned grid, unsigned block, size_t smem, K k
         cudaError_t _e = (expr);           \
         if (_e != cudaSuccess) return _e;  \
     } while (0)
-#define BZ_NOTE_LAUNCH() ((void)0)
 
 // dynamic shared memory: kernels declare it with BZ_DYN_SMEM(type, name)
 #define BZ_DYN_SMEM(type, name) type* const name = reinterpret_cast<type*>(::emu::g_dyn_smem)

@@ -1,0 +1,168 @@
+"""The WHOLE library on the CPU thread-block emulator: bzip3_b200/csrc/bz3_api.cu -- the C ABI, the block framing and
+validation, every launch sequence and every kernel -- compiled by g++ on top of tests/native/cta_emu.h into
+tests/_build/libbzip3_emu.so and driven through the same Python binding as the GPU library.
+
+Test infrastructure: it lets the "no GPU" suite check the product's host logic and kernels against the oracle on small
+inputs (the emulator codes a few kilobytes per second).  The GPU parity tests remain the gate for the real library;
+what runs here is the same source, not the same binary."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import bzip3_b200
+from bzip3_b200 import synth
+from tests import refs
+from tests.test_oracle import hostile_variants
+
+ROOT = refs.ROOT
+SO = os.path.join(ROOT, "tests", "_build", "libbzip3_emu.so")
+CSRC = os.path.join(ROOT, "bzip3_b200", "csrc")
+EMU_H = os.path.join(ROOT, "tests", "native", "cta_emu.h")
+SRCS = [os.path.join(CSRC, "bz3_api.cu"), os.path.join(ROOT, "tests", "native", "cta_emu.cpp")]
+BS = 65 * 1024 + 1024   # smallest legal block size is 65 KiB (src/libbz3.c:536)
+CUT = 2000              # bytes per case: the emulated suffix sort does ~3 KB/s
+
+
+def build_emulated_library():
+    deps = SRCS + [EMU_H] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(ROOT, "include", "libbz3.h"), os.path.join(ROOT, "include", "bz3_b200.h")]
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DBZ_EMU", "-include",
+                               EMU_H, "-x", "c++", "-o", SO] + SRCS + ["-lpthread"])
+    return SO
+
+
+@pytest.fixture(scope="module")
+def emulib():
+    """Points the Python binding at the emulated library for the tests of this module, then restores it."""
+    so = build_emulated_library()
+    saved = (bzip3_b200.LIB_PATH, bzip3_b200._lib)
+    bzip3_b200.LIB_PATH, bzip3_b200._lib = so, None
+    try:
+        yield bzip3_b200.lib()
+    finally:
+        bzip3_b200.LIB_PATH, bzip3_b200._lib = saved
+
+
+@pytest.fixture(scope="module")
+def st(emulib):
+    with bzip3_b200.Bz3State(BS) as s:
+        yield s
+
+
+CASES = [(name, bytes(d[:CUT])) for name, d in synth.edge_cases()]
+IDS = [c[0] for c in CASES]
+
+
+@pytest.mark.parametrize("name,data", CASES, ids=IDS)
+def test_block_roundtrip_vs_oracle(st, name, data):
+    enc_o, r_o, e_o = refs.oracle_encode_block(data, BS)
+    enc_g, r_g = st.encode_block(data)
+    assert r_g == r_o, (r_g, r_o, st.last_error)
+    if len(data) >= 64:
+        assert st.last_error == e_o
+    assert enc_g == enc_o
+    dec, r = st.decode_block(enc_o, len(data))
+    assert r == len(data) and dec == data
+    if len(data) >= 64:
+        assert st.last_error == 0
+
+
+@pytest.mark.parametrize("enc_v,dec_v,lzp_v", [(4, 4, 0), (6, 9, 2), (6, 5, 2), (0, 8, 2)])
+def test_block_roundtrip_with_other_kernels(st, enc_v, dec_v, lzp_v):
+    """The opt-in entropy / LZP kernels selected through the block API give the same bytes."""
+    L = st.L
+    datas = [synth.zipf_text(1800, seed=3).tobytes(), synth.log_stream(2500, seed=4).tobytes(),
+             bytes(np.repeat(np.arange(40, dtype=np.uint8), 50)), synth.source_corpus(2400, seed=6).tobytes()]
+    L.bz3_b200_set_variant(st.handle, 5 + 100, enc_v)
+    L.bz3_b200_set_variant(st.handle, 5 + 200, dec_v)
+    L.bz3_b200_set_variant(st.handle, 3, lzp_v)
+    try:
+        assert L.bz3_b200_get_variant(st.handle, 5 + 100) == enc_v and L.bz3_b200_get_variant(st.handle, 5 + 200) == dec_v
+        for data in datas:
+            enc_o, r_o, _ = refs.oracle_encode_block(data, BS)
+            enc_g, r_g = st.encode_block(data)
+            assert r_g == r_o and enc_g == enc_o
+            dec, r = st.decode_block(enc_o, len(data))
+            assert r == len(data) and dec == data
+    finally:
+        L.bz3_b200_set_variant(st.handle, 5, 0)
+        L.bz3_b200_set_variant(st.handle, 3, 0)
+
+
+def test_block_too_big_and_raw_paths(st):
+    enc, r = st.encode_block(bytes(BS + 1))
+    assert r == -1 and st.last_error == bzip3_b200.BZ3_ERR_DATA_TOO_BIG
+    enc, r = st.encode_block(b"tiny")  # the reference returns early without touching last_error (src/libbz3.c:596-601)
+    assert r == 12 and st.last_error == bzip3_b200.BZ3_ERR_DATA_TOO_BIG
+    dec, r = st.decode_block(enc, 4)
+    assert dec == b"tiny" and st.last_error == bzip3_b200.BZ3_ERR_DATA_TOO_BIG
+
+
+@pytest.mark.parametrize("name", ["raw63", "coded65_text", "zeros_4k", "random_10k", "long_runs", "escape_heavy"])
+def test_hostile_decode_error_parity(st, name):
+    """Truncated, bit-flipped and header-patched blocks: same return value, error number and bytes as the oracle."""
+    data = dict(CASES)[name][:1200]
+    enc, r, e = refs.oracle_encode_block(data, BS)
+    rng = np.random.default_rng(len(data))
+    for k, (venc, osz, bsz, csz) in enumerate(hostile_variants(enc, len(data), BS, rng)):
+        want = refs.oracle_decode_block(venc, osz, BS, buffer_size=bsz, compressed_size=csz, err_init=55)
+        got_bytes, got_r = st.decode_block(venc, osz, buffer_size=bsz, compressed_size=csz)
+        assert got_r == want[1], (name, k, got_r, want[1:], st.last_error)
+        if want[2] != 55:  # the oracle wrote an error code
+            assert st.last_error == want[2], (name, k, st.last_error, want[2])
+        if got_r >= 0:
+            assert got_bytes == want[0], (name, k)
+
+
+def test_batch_api_uses_threads_and_matches_single_blocks(emulib):
+    L = emulib
+    datas = [synth.zipf_text(1500, seed=5).tobytes(), synth.log_stream(1200, seed=6).tobytes(), b"short",
+             bytes(np.random.default_rng(3).integers(0, 256, 900, dtype=np.uint8))]
+    states = [bzip3_b200.Bz3State(BS) for _ in datas]
+    try:
+        bufs = []
+        for d in datas:
+            b = np.zeros(bzip3_b200.bound(BS) + 64, np.uint8)
+            b[:len(d)] = np.frombuffer(d, np.uint8)
+            bufs.append(b)
+        sizes = [len(d) for d in datas]
+        out_sizes = bzip3_b200.encode_blocks(states, bufs, sizes)
+        for d, b, r in zip(datas, bufs, out_sizes):
+            enc_o, r_o, _ = refs.oracle_encode_block(d, BS)
+            assert r == r_o and bytes(b[:r]) == enc_o
+        errs = bzip3_b200.decode_blocks(states, bufs, [len(b) for b in bufs], out_sizes, sizes)
+        for d, b, e in zip(datas, bufs, errs):
+            assert e == 0 and bytes(b[:len(d)]) == d
+    finally:
+        for s in states:
+            s.close()
+
+
+def test_frame_api_and_helpers(emulib):
+    L = emulib
+    data = synth.zipf_text(2200, seed=9)
+    n = len(data)
+    cap = bzip3_b200.bound(n) + 64
+    out = np.zeros(cap, np.uint8)
+    osz = C.c_size_t(cap)
+    assert L.bz3_compress(BS, refs.ptr(data), refs.ptr(out), n, C.byref(osz)) == 0
+    frame = out[:osz.value].copy()
+    assert bytes(frame[:5]) == b"BZ3v1"
+    back = np.zeros(n + 64, np.uint8)
+    bsz = C.c_size_t(n + 64)
+    assert L.bz3_decompress(refs.ptr(frame), refs.ptr(back), len(frame), C.byref(bsz)) == 0
+    assert bsz.value == n and bytes(back[:n]) == bytes(data)
+    # the same frame from the reference, when it was built here
+    if refs.have_ref():
+        R = refs.ref()
+        out_r = np.zeros(cap, np.uint8)
+        osz_r = C.c_size_t(cap)
+        assert R.bz3_compress(BS, refs.ptr(data), refs.ptr(out_r), n, C.byref(osz_r)) == 0
+        assert osz_r.value == osz.value and bytes(out_r[:osz_r.value]) == bytes(frame)
+    assert L.bz3_bound(1000) == 1000 + 1000 // 50 + 32
+    assert not L.bz3_new(1000) and not L.bz3_new((511 << 20) + 1)   # block size out of range
