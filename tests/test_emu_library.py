@@ -23,7 +23,7 @@ CSRC = os.path.join(ROOT, "bzip3_b200", "csrc")
 EMU_H = os.path.join(ROOT, "tests", "native", "cta_emu.h")
 SRCS = [os.path.join(CSRC, "bz3_api.cu"), os.path.join(ROOT, "tests", "native", "cta_emu.cpp")]
 BS = 65 * 1024 + 1024   # smallest legal block size is 65 KiB (src/libbz3.c:536)
-CUT = 2000              # bytes per case: the emulated suffix sort does ~3 KB/s
+CUT = 1400              # bytes per case: the emulated suffix sort does ~3 KB/s
 
 
 def build_emulated_library():
@@ -76,8 +76,8 @@ def test_block_roundtrip_vs_oracle(st, name, data):
 def test_block_roundtrip_with_other_kernels(st, enc_v, dec_v, lzp_v):
     """The opt-in entropy / LZP kernels selected through the block API give the same bytes."""
     L = st.L
-    datas = [synth.zipf_text(1800, seed=3).tobytes(), synth.log_stream(2500, seed=4).tobytes(),
-             bytes(np.repeat(np.arange(40, dtype=np.uint8), 50)), synth.source_corpus(2400, seed=6).tobytes()]
+    datas = [synth.zipf_text(1500, seed=3).tobytes(), synth.log_stream(2000, seed=4).tobytes(),
+             bytes(np.repeat(np.arange(40, dtype=np.uint8), 40))]
     L.bz3_b200_set_variant(st.handle, 5 + 100, enc_v)
     L.bz3_b200_set_variant(st.handle, 5 + 200, dec_v)
     L.bz3_b200_set_variant(st.handle, 3, lzp_v)
@@ -103,7 +103,7 @@ def test_block_too_big_and_raw_paths(st):
     assert dec == b"tiny" and st.last_error == bzip3_b200.BZ3_ERR_DATA_TOO_BIG
 
 
-@pytest.mark.parametrize("name", ["raw63", "coded65_text", "zeros_4k", "random_10k", "long_runs", "escape_heavy"])
+@pytest.mark.parametrize("name", ["raw63", "coded65_text", "random_10k", "escape_heavy"])
 def test_hostile_decode_error_parity(st, name):
     """Truncated, bit-flipped and header-patched blocks: same return value, error number and bytes as the oracle."""
     data = dict(CASES)[name][:1200]

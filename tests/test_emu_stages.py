@@ -89,7 +89,7 @@ def test_mrle_kernels(name, data):
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_bwt_and_inverse(name, data):
     E, O = emu(), refs.oracle()
-    a = data[:2500]
+    a = data[:1500]
     n = len(a)
     pad = np.zeros(n + 64, np.uint8)
     pad[:n] = a
