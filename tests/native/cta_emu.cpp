@@ -4,6 +4,10 @@
 
 #include <mutex>
 
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
+
 namespace emu {
 Cta* g_cta = nullptr;
 Fiber* g_cur = nullptr;
@@ -82,6 +86,10 @@ void launch(Dim3 grid, Dim3 block, size_t dyn_smem_bytes, const std::function<vo
                     f.tid.y = (t / block.x) % block.y;
                     f.tid.z = t / (block.x * block.y);
                     f.stack = get_stack(t);
+#if defined(__SANITIZE_ADDRESS__)
+                    // fibers of the previous launch left by switching away, never unwinding: their redzones are stale
+                    __asan_unpoison_memory_region(f.stack, kStackBytes);
+#endif
                     uintptr_t top = ((uintptr_t)f.stack + kStackBytes) & ~(uintptr_t)15;
                     uintptr_t* a = (uintptr_t*)(top - 16);  // 16-byte aligned slot of the first return address
                     a[0] = (uintptr_t)&emu_fiber_main;

@@ -1,0 +1,56 @@
+"""Memory check of the whole library without a GPU: builds bzip3_b200/csrc/bz3_api.cu for the CPU thread-block
+emulator (tests/native/cta_emu.h) with -fsanitize=address and round-trips every edge case of the test corpus through
+the block API with the default and the opt-in kernels.  "Device" buffers are heap blocks there and shared memory is
+ordinary memory, so an out-of-bounds access of any kernel is an AddressSanitizer report.
+
+    python tools/emu_asan.py        (re-executes itself with libasan preloaded)
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = "/tmp/libbzip3_emu_asan.so"
+
+
+def main():
+    if os.environ.get("BZ3_EMU_ASAN_CHILD") != "1":
+        emu_h = os.path.join(ROOT, "tests", "native", "cta_emu.h")
+        subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-std=c++17", "-fPIC",
+                               "-shared", "-fvisibility=hidden", "-DBZ_EMU", "-include", emu_h, "-x", "c++", "-o", SO,
+                               os.path.join(ROOT, "bzip3_b200", "csrc", "bz3_api.cu"),
+                               os.path.join(ROOT, "tests", "native", "cta_emu.cpp"), "-lpthread"])
+        asan = subprocess.check_output(["g++", "-print-file-name=libasan.so"], text=True).strip()
+        env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0",
+                   BZ3_EMU_ASAN_CHILD="1", BZ3_B200_LIB=SO)
+        return subprocess.call([sys.executable, os.path.abspath(__file__)], env=env)
+    sys.path.insert(0, ROOT)
+    import bzip3_b200
+    from bzip3_b200 import synth
+    from tests import refs
+    bs = 65 * 1024 + 1024
+    cases = [(n, bytes(d[:1200])) for n, d in synth.edge_cases()]
+    with bzip3_b200.Bz3State(bs) as s:
+        for enc_v, dec_v, lzp_v in ((0, 0, 0), (6, 9, 2), (4, 4, 0), (6, 5, 2), (0, 8, 2), (6, 7, 0), (6, 6, 2)):
+            s.L.bz3_b200_set_variant(s.handle, 105, enc_v)
+            s.L.bz3_b200_set_variant(s.handle, 205, dec_v)
+            s.L.bz3_b200_set_variant(s.handle, 3, lzp_v)
+            for name, data in cases:
+                enc, r = s.encode_block(data)
+                want = refs.oracle_encode_block(data, bs)
+                assert r == want[1] and enc == want[0], (enc_v, dec_v, lzp_v, name)
+                dec, r2 = s.decode_block(enc, len(data))
+                assert dec == data, (enc_v, dec_v, lzp_v, name)
+                if len(enc) > 40:   # a damaged block must not make any kernel read or write out of bounds either
+                    bad = bytearray(enc)
+                    bad[len(bad) // 2] ^= 0x10
+                    s.decode_block(bytes(bad), len(data))
+                    s.decode_block(enc[: len(enc) // 2], len(data))
+            print("encoder %d / decoder %d / LZP %d: %d cases round-tripped, no AddressSanitizer report" % (
+                enc_v, dec_v, lzp_v, len(cases)), flush=True)
+    print("done")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
