@@ -15,6 +15,7 @@ Dim3 g_blockIdx, g_blockDim, g_gridDim;
 unsigned char* g_dyn_smem = nullptr;
 int g_schedule = 0;
 uint64_t g_rng = 88172645463325252ull;
+char g_tsan_token = 0;
 }  // namespace emu
 
 // void emu_switch(void** save_sp, void* load_sp): save the callee-saved registers of the running fiber
@@ -62,6 +63,7 @@ static std::mutex g_launch_mutex;   // one grid at a time: the emulator state an
 
 void launch(Dim3 grid, Dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {
     std::lock_guard<std::mutex> lock(g_launch_mutex);
+    BZ_TSAN_INTERNAL();
     const unsigned nthreads = block.x * block.y * block.z;
     if (nthreads == 0 || nthreads > (unsigned)kMaxThreads) { fprintf(stderr, "[cta_emu] bad block size\n"); abort(); }
     if (dyn_smem_bytes + 64 > g_smem_cap) {
@@ -86,6 +88,9 @@ void launch(Dim3 grid, Dim3 block, size_t dyn_smem_bytes, const std::function<vo
                     f.tid.y = (t / block.x) % block.y;
                     f.tid.z = t / (block.x * block.y);
                     f.stack = get_stack(t);
+#if defined(__SANITIZE_THREAD__)
+                    f.tsan = __tsan_create_fiber(0);
+#endif
 #if defined(__SANITIZE_ADDRESS__)
                     // fibers of the previous launch left by switching away, never unwinding: their redzones are stale
                     __asan_unpoison_memory_region(f.stack, kStackBytes);
@@ -105,7 +110,16 @@ void launch(Dim3 grid, Dim3 block, size_t dyn_smem_bytes, const std::function<vo
                 g_cta = &cta;
                 cta.cur = 0;
                 g_cur = &cta.fibers[0];
+#if defined(__SANITIZE_THREAD__)
+                cta.main_tsan = __tsan_get_current_fiber();
+                __tsan_release(&g_tsan_token);      // everything the host did so far happens before the grid
+#endif
+                BZ_TSAN_SWITCH(g_cur->tsan);
                 emu_switch(&cta.main_sp, g_cur->sp);
+#if defined(__SANITIZE_THREAD__)
+                __tsan_acquire(&g_tsan_token);      // ... and the grid happens before what the host does next
+                for (auto& f : cta.fibers) __tsan_destroy_fiber(f.tsan);
+#endif
                 for (auto& f : cta.fibers)
                     if (!f.done) { fprintf(stderr, "[cta_emu] a thread never finished\n"); abort(); }
                 g_cta = nullptr;

@@ -23,6 +23,38 @@
 #include <vector>
 #include <sys/mman.h>
 
+// ThreadSanitizer build (tools/emu_tsan.py): every CUDA thread is announced to TSan as a fiber and every barrier /
+// warp collective as a release-acquire edge, so a shared- or global-memory access pair of two CUDA threads with no
+// barrier, collective or atomic between them is reported as a data race -- a race check without a GPU.
+#if defined(__SANITIZE_THREAD__)
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+void AnnotateIgnoreReadsBegin(const char* file, int line);
+void AnnotateIgnoreReadsEnd(const char* file, int line);
+void AnnotateIgnoreWritesBegin(const char* file, int line);
+void AnnotateIgnoreWritesEnd(const char* file, int line);
+}
+// the emulator's own bookkeeping (scheduler state, collective slots) is shared by all fibers on purpose
+struct BzTsanIgnore {
+    BzTsanIgnore() { AnnotateIgnoreReadsBegin(__FILE__, __LINE__); AnnotateIgnoreWritesBegin(__FILE__, __LINE__); }
+    ~BzTsanIgnore() { AnnotateIgnoreWritesEnd(__FILE__, __LINE__); AnnotateIgnoreReadsEnd(__FILE__, __LINE__); }
+};
+#define BZ_TSAN_INTERNAL() BzTsanIgnore _bz_tsan_ignore
+#define BZ_TSAN_SWITCH(f) __tsan_switch_to_fiber((f), 1) /* 1 = no implied synchronisation between the fibers */
+#define BZ_TSAN_RELEASE(a) __tsan_release((void*)(a))
+#define BZ_TSAN_ACQUIRE(a) __tsan_acquire((void*)(a))
+#else
+#define BZ_TSAN_SWITCH(f) ((void)0)
+#define BZ_TSAN_RELEASE(a) ((void)0)
+#define BZ_TSAN_ACQUIRE(a) ((void)0)
+#define BZ_TSAN_INTERNAL() ((void)0)
+#endif
+
 namespace emu {
 
 struct Dim3 {
@@ -43,6 +75,7 @@ struct NamedBarrier {
     unsigned arrived = 0;
     unsigned gen = 0;
     unsigned orv = 0, last_or = 0;
+    char tsan_token[2] = {0, 0};   // release/acquire object of the even / odd generations (see bar_sync_impl)
 };
 
 struct Fiber {
@@ -50,6 +83,7 @@ struct Fiber {
     char* stack = nullptr;
     Dim3 tid;
     bool done = false;
+    void* tsan = nullptr;                // ThreadSanitizer's handle of this fiber
     const void* waiting_on = nullptr;    // barrier / collective slot this fiber sleeps on (not scheduled meanwhile)
     std::map<uint32_t, unsigned> phase;  // per-mask count of warp collectives executed
 };
@@ -61,6 +95,7 @@ struct Cta {
     unsigned live = 0;
     std::function<void()> body;
     void* main_sp = nullptr;
+    void* main_tsan = nullptr;
     int cur = -1;
     unsigned long long switches = 0;
 };
@@ -69,6 +104,8 @@ extern Cta* g_cta;
 extern Fiber* g_cur;
 extern Dim3 g_blockIdx, g_blockDim, g_gridDim;
 extern unsigned char* g_dyn_smem;
+extern char g_tsan_token;   // host -> thread, thread -> host and CTA -> next CTA edges (CTAs of a grid run one after another
+                            // here and share the static "shared" arrays, so races BETWEEN CTAs are out of this check's reach)
 extern int g_schedule;  // 0 round robin ascending, 1 descending, 2 pseudo random
 extern uint64_t g_rng;
 
@@ -110,6 +147,7 @@ inline void wake_all(const void* obj) {
 inline void sleep_on(const void* obj, const char* what);
 
 inline void yield() {
+    BZ_TSAN_INTERNAL();
     Cta& c = *g_cta;
     const int nxt = pick_next();
     if (nxt < 0 || nxt == c.cur) return;
@@ -117,6 +155,7 @@ inline void yield() {
     c.cur = nxt;
     g_cur = &c.fibers[nxt];
     c.switches++;
+    BZ_TSAN_SWITCH(g_cur->tsan);
     emu_switch(&from->sp, g_cur->sp);
 }
 
@@ -129,28 +168,48 @@ inline void sleep_on(const void* obj, const char* what) {
     c.cur = nxt;
     g_cur = &c.fibers[nxt];
     c.switches++;
+    BZ_TSAN_SWITCH(g_cur->tsan);
     emu_switch(&from->sp, g_cur->sp);
 }
 
 [[noreturn]] inline void fiber_exit() {
-    Cta& c = *g_cta;
-    g_cur->done = true;
-    c.live--;
-    for (auto& f : c.fibers) f.waiting_on = nullptr;   // an exit can complete a barrier: let sleepers re-check
-    const int nxt = pick_next();
-    void* dummy;
-    if (nxt < 0) {
-        emu_switch(&dummy, c.main_sp);
-    } else {
-        c.cur = nxt;
-        g_cur = &c.fibers[nxt];
-        emu_switch(&dummy, g_cur->sp);
+    void* next_sp;
+    void* next_tsan;
+    {
+        BZ_TSAN_INTERNAL();   // must end before the last switch: this fiber never comes back
+        Cta& c = *g_cta;
+        BZ_TSAN_RELEASE(&g_tsan_token);
+        g_cur->done = true;
+        c.live--;
+        for (auto& f : c.fibers) f.waiting_on = nullptr;   // an exit can complete a barrier: let sleepers re-check
+        const int nxt = pick_next();
+        if (nxt < 0) {
+            next_sp = c.main_sp;
+            next_tsan = c.main_tsan;
+        } else {
+            c.cur = nxt;
+            g_cur = &c.fibers[nxt];
+            next_sp = g_cur->sp;
+            next_tsan = g_cur->tsan;
+        }
     }
+    (void)next_tsan;
+    void* dummy;
+    BZ_TSAN_SWITCH(next_tsan);
+    emu_switch(&dummy, next_sp);
     abort();
 }
 
 extern "C" inline void emu_fiber_main() {
-    g_cta->body();
+    BZ_TSAN_ACQUIRE(&g_tsan_token);
+    {
+        std::function<void()>* body;
+        {
+            BZ_TSAN_INTERNAL();
+            body = &g_cta->body;
+        }
+        (*body)();
+    }
     fiber_exit();
 }
 
@@ -158,11 +217,15 @@ extern "C" inline void emu_fiber_main() {
 // bar id 0 with count 0 == __syncthreads: all live (not yet exited) threads.  A watchdog aborts when a
 // barrier can never complete (every live thread is waiting on something).
 inline unsigned bar_sync_impl(int id, unsigned count, unsigned pred, bool wait) {
+    BZ_TSAN_INTERNAL();
     Cta& c = *g_cta;
     NamedBarrier& b = c.bars[id];
     const unsigned gen = b.gen;
     b.arrived++;
     b.orv |= pred;
+    // the edge belongs to THIS generation: a thread that already left and arrived at the next barrier must not
+    // lend its later writes to a thread that is only now waking up from this one
+    BZ_TSAN_RELEASE(&b.tsan_token[gen & 1]);
     for (;;) {
         const unsigned need = count ? count : c.live;
         if (b.gen != gen) break;
@@ -177,6 +240,7 @@ inline unsigned bar_sync_impl(int id, unsigned count, unsigned pred, bool wait) 
         if (!wait) return 0;
         sleep_on(&b, "barrier");
     }
+    BZ_TSAN_ACQUIRE(&b.tsan_token[gen & 1]);
     return b.last_or;
 }
 
@@ -191,6 +255,7 @@ inline unsigned warp_of(const Fiber* f) { return f->tid.x >> 5; }
 
 template <class R>
 inline auto warp_collective(uint32_t mask, uint64_t mine, R reader) -> decltype(reader((const uint64_t*)nullptr)) {
+    BZ_TSAN_INTERNAL();
     Fiber* f = g_cur;
     const unsigned lane = lane_of(f);
     const uint32_t bit = 1u << lane;
@@ -207,9 +272,11 @@ inline auto warp_collective(uint32_t mask, uint64_t mine, R reader) -> decltype(
     }
     s.val[lane] = mine;
     s.arrived |= bit;
+    BZ_TSAN_RELEASE(&s);
     if ((s.arrived & mask) == mask) wake_all(&s);
     // lanes of the mask that already exited can never arrive: that is a bug and ends in the deadlock report
     while ((s.arrived & mask) != mask) sleep_on(&s, "warp collective");
+    BZ_TSAN_ACQUIRE(&s);
     auto r = reader(s.val);
     s.consumed |= bit;
     if ((s.consumed & mask) == mask) {
@@ -355,14 +422,25 @@ inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline void __stcg(T* p, T v) { *p = v; }
-template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
-template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
-template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
-template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
-template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return o; }
-template <class T> inline T atomicXor(T* p, T v) { T o = *p; *p = o ^ v; return o; }
-template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
-template <class T> inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+template <class T> inline T atomicMax(T* p, T v) {
+    T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
+template <class T> inline T atomicMin(T* p, T v) {
+    T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
+template <class T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicAnd(T* p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicXor(T* p, T v) { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicCAS(T* p, T c, T v) {
+    __atomic_compare_exchange_n(p, &c, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return c;
+}
 inline long long clock64() { return (long long)::emu::g_cta->switches; }
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> inline T max(T a, T b) { return a > b ? a : b; }
