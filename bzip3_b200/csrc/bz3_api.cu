@@ -4,8 +4,11 @@
 // headers included below.  Stage order, header layout, validation order and error numbers restate
 // bz3_encode_block / bz3_decode_block (reference src/libbz3.c:585-809); the batch entry points restate
 // bz3_encode_blocks / bz3_decode_blocks (:813-872) with one host thread + one CUDA stream per block.
+#include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -82,7 +85,8 @@ struct bz3_state {
     s32 sort_rounds;
     double sort_ms;
     int variant[BZ3_STAGE_COUNT];
-    int cm_enc, cm_dec;   // entropy-stage kernel selection (see kCmEncDefault / kCmDecDefault)
+    int cm_enc, cm_dec;   // entropy-stage kernel selection in effect (see kernel_autoselect)
+    int lzp_default;      // LZP kernels used when variant[BZ3_STAGE_LZP] == 0
     cudaEvent_t sort_ev[2 * 40];
 };
 
@@ -185,9 +189,10 @@ cudaError_t run_rle_decode(bz3_state* s, const u8* d_in, u32 maxin, u8* d_out, u
 cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* result) {
     if (n < kLzpMinMatch + 32) { *result = -1; return cudaSuccess; }
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
-    if (s->variant[BZ3_STAGE_LZP] == 1)
+    const int lzp_v = s->variant[BZ3_STAGE_LZP] ? s->variant[BZ3_STAGE_LZP] : s->lzp_default;
+    if (lzp_v == 1)
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_serial_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
-    else if (s->variant[BZ3_STAGE_LZP] == 2)   // several windows in flight (opt-in until timed on the GPU)
+    else if (lzp_v == 2)   // several windows in flight
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_pf_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
@@ -202,9 +207,10 @@ cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* 
 cudaError_t run_lzp_decode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32 max, s32* result) {
     if (n < 4) { *result = -1; return cudaSuccess; }
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
-    if (s->variant[BZ3_STAGE_LZP] == 1)
+    const int lzp_v = s->variant[BZ3_STAGE_LZP] ? s->variant[BZ3_STAGE_LZP] : s->lzp_default;
+    if (lzp_v == 1)
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_decode_serial_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
-    else if (s->variant[BZ3_STAGE_LZP] == 2)   // bulk decoder (opt-in until timed on the GPU)
+    else if (lzp_v == 2)   // bulk decoder
         BZ_LAUNCH(1, kLzpBulkThreads, 0, s->stream, lzp_decode_bulk_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_decode_warp_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
@@ -266,13 +272,24 @@ cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, i
 //            5 all paths, one multiply per level                 6 walker warps (walk of 5) + model threads of 0/4
 //            7 = 6 with the slim model-thread loop               8 = 7, walker warps stop after three levels
 //            9 = 8 with the branch-light, parity-unrolled model-thread loop
-// Defaults can be overridden per process with BZ3_B200_CM_ENC / BZ3_B200_CM_DEC (tuning, tests).
-constexpr int kCmEncDefault = 0;
-constexpr int kCmDecDefault = 0;
+// LZP (BZ3_STAGE_LZP): 0 = the default in effect, 1 single lane, 2 windows in flight / bulk decoder, 3 one window per step.
+// Defaults: see kernel_autoselect(); fixed per process with BZ3_B200_CM_ENC / BZ3_B200_CM_DEC / BZ3_B200_LZP.
+// The defaults are not constants: the first bz3_new() of a process runs a short self-test on the device
+// (kernel_autoselect below) that lets the newer kernels replace the proven ones only if they reproduce the proven
+// kernels' bytes on the test inputs AND are faster there.
+struct KernelChoice {
+    int cm_enc = 0, cm_dec = 0, lzp = 3;   // proven kernels: chunked encoder 0, tree decoder 0, one-window LZP (3)
+};
+KernelChoice g_choice;
+std::once_flag g_choice_once;
 
 int env_int(const char* name, int fallback) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : fallback;
+}
+bool env_set(const char* name) {
+    const char* v = getenv(name);
+    return v && *v;
 }
 
 cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* out_size) {
@@ -494,6 +511,171 @@ BZIP3_API const char* bz3_strerror(struct bz3_state* state) {  // reference src/
     }
 }
 
+// ------------------------------------------------------------------ choice of the default kernels
+// Runs once per process, on the first state, before the state is handed to the caller.  The proven kernels
+// (entropy encoder 0 / decoder 0, one-window LZP) are the reference: a newer kernel becomes the default only if it
+// reproduces their bytes on every test input -- full and truncated streams -- and needs less time there.
+// Environment: BZ3_B200_CM_ENC / BZ3_B200_CM_DEC / BZ3_B200_LZP pin a stage; BZ3_B200_AUTOSELECT=0 keeps the proven
+// kernels, =force accepts a newer kernel that is correct without asking the clock (emulator, experiments).
+namespace {
+
+void selftest_bytes(u8* p, s32 n, u32 seed) {   // deterministic input with runs, skewed symbols and a noisy stretch
+    u32 x = seed * 2654435761u + 12345u;
+    s32 i = 0;
+    while (i < n) {
+        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+        const u32 kind = x & 7u;
+        u8 sym = (kind < 5) ? (u8)("etaoin shrdlu"[(x >> 8) % 13]) : (u8)(x >> 16);
+        s32 run = (kind == 0) ? (s32)((x >> 24) & 63u) + 1 : (kind < 3 ? (s32)((x >> 24) & 3u) + 1 : 1);
+        if (i > n / 2 && i < n / 2 + n / 8) { sym = (u8)(x >> 9); run = 1; }   // incompressible stretch
+        while (run-- > 0 && i < n) p[i++] = sym;
+    }
+}
+
+double seconds_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct SelfTest {
+    bz3_state* s;
+    std::vector<u8> a, b;   // host staging
+    bool h2d(const u8* h, u8* d, size_t n) {
+        return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s->stream) == cudaSuccess && cudaStreamSynchronize(s->stream) == cudaSuccess;
+    }
+    bool d2h(u8* h, const u8* d, size_t n) {
+        return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess && cudaStreamSynchronize(s->stream) == cudaSuccess;
+    }
+    // entropy encoder `v` on d_buf[0][0..n) -> d_buf[1]; returns size (<0 on failure), bytes in `out`, best time of two
+    s32 cm_encode(int v, s32 n, std::vector<u8>& out, double& best) {
+        s->cm_enc = v;
+        s32 size = -1;
+        best = 1e30;
+        for (int rep = 0; rep < 2; rep++) {
+            const double t0 = seconds_now();
+            if (run_cm_encode(s, s->d_buf[0], n, s->d_buf[1], &size) != cudaSuccess || size <= 0 || (size_t)size > s->cap) return -1;
+            best = std::min(best, seconds_now() - t0);
+        }
+        out.assign((size_t)size, 0);
+        return d2h(out.data(), s->d_buf[1], (size_t)size) ? size : -1;
+    }
+    // entropy decoder `v` on d_buf[1][0..insize) -> d_buf[2][0..n)
+    bool cm_decode(int v, s32 insize, s32 n, std::vector<u8>& out, double& best) {
+        s->cm_dec = v;
+        best = 1e30;
+        for (int rep = 0; rep < 2; rep++) {
+            const double t0 = seconds_now();
+            if (run_cm_decode(s, s->d_buf[1], insize, s->d_buf[2], n) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) return false;
+            best = std::min(best, seconds_now() - t0);
+        }
+        out.assign((size_t)n, 0);
+        return d2h(out.data(), s->d_buf[2], (size_t)n);
+    }
+};
+
+void kernel_autoselect(bz3_state* s) {
+    KernelChoice c;   // the proven kernels
+    const char* mode = getenv("BZ3_B200_AUTOSELECT");
+    const bool off = mode && mode[0] == '0';
+    const bool force = mode && mode[0] == 'f';
+    const bool pin_enc = env_set("BZ3_B200_CM_ENC"), pin_dec = env_set("BZ3_B200_CM_DEC"), pin_lzp = env_set("BZ3_B200_LZP");
+    if (pin_enc) c.cm_enc = env_int("BZ3_B200_CM_ENC", 0);
+    if (pin_dec) c.cm_dec = env_int("BZ3_B200_CM_DEC", 0);
+    if (pin_lzp) c.lzp = env_int("BZ3_B200_LZP", 3);
+    if (!off) {
+#if defined(BZ_EMU)
+        const s32 n = 3000;    // the CPU emulator codes a few kilobytes per second
+#else
+        const s32 n = 48 * 1024;
+#endif
+        constexpr int kNewEnc = 6, kNewDec = 8, kNewLzp = 2;
+        SelfTest T{s};
+        std::vector<u8> x((size_t)n + 64, 0), ref, cand, back;
+        selftest_bytes(x.data(), n, 20260923u);
+        double t_ref = 0, t_new = 0;
+        // ---- entropy stage
+        s32 r0 = -1;
+        if (T.h2d(x.data(), s->d_buf[0], (size_t)n + 64)) r0 = T.cm_encode(0, n, ref, t_ref);
+        bool base_ok = r0 > 0 && T.cm_decode(0, r0, n, back, t_new) && memcmp(back.data(), x.data(), (size_t)n) == 0;
+        if (base_ok && !pin_enc) {
+            const s32 r1 = T.cm_encode(kNewEnc, n, cand, t_new);
+            if (r1 == r0 && memcmp(cand.data(), ref.data(), (size_t)r0) == 0 && (force || t_new < 0.9 * t_ref)) c.cm_enc = kNewEnc;
+            T.h2d(ref.data(), s->d_buf[1], (size_t)r0);   // the decoders below read the proven encoder's stream
+        }
+        if (base_ok && !pin_dec) {
+            std::vector<u8> full0, full1, cut0, cut1;
+            double t0d = 0, t1d = 0, tt = 0;
+            bool ok = T.cm_decode(0, r0, n, full0, t0d) && T.cm_decode(kNewDec, r0, n, full1, t1d) && full0 == full1 &&
+                      memcmp(full1.data(), x.data(), (size_t)n) == 0;
+            // truncated stream: the decoders must agree on the garbage as well (read_in() past the end, src/libbz3.c:345)
+            ok = ok && T.cm_decode(0, r0 / 2, n, cut0, tt) && T.cm_decode(kNewDec, r0 / 2, n, cut1, tt) && cut0 == cut1;
+            ok = ok && T.cm_decode(0, 5, n, cut0, tt) && T.cm_decode(kNewDec, 5, n, cut1, tt) && cut0 == cut1;
+            if (ok && (force || t1d < 0.9 * t0d)) c.cm_dec = kNewDec;
+        }
+        // ---- LZP: an input with long matches, escapes and literal stretches
+        if (!pin_lzp) {
+            std::vector<u8> y((size_t)n + 64, 0);
+            selftest_bytes(y.data(), n, 777u);
+            for (s32 i = n / 3; i + 600 < n; i += 1700) memcpy(y.data() + i, y.data() + i / 4, 600);   // repeats
+            for (s32 i = 50; i < n; i += 997) y[(size_t)i] = (u8)kLzpEscape;
+            std::vector<u8> e0, e1, d0, d1;
+            s32 z0 = -2, z1 = -2, w0 = -2, w1 = -2;
+            double te0 = 1e30, te1 = 1e30, td0 = 1e30, td1 = 1e30;
+            bool ok = true;
+            for (int v : {3, kNewLzp}) {
+                s->lzp_default = v;
+                s32& z = (v == 3) ? z0 : z1;
+                double& te = (v == 3) ? te0 : te1;
+                std::vector<u8>& e = (v == 3) ? e0 : e1;
+                for (int rep = 0; rep < 2 && ok; rep++) {
+                    ok = T.h2d(y.data(), s->d_buf[0], (size_t)n + 64);
+                    const double t0 = seconds_now();
+                    ok = ok && run_lzp_encode(s, s->d_buf[0], n, s->d_buf[1], &z) == cudaSuccess;
+                    te = std::min(te, seconds_now() - t0);
+                }
+                if (ok && z > 0 && (size_t)z <= s->cap) { e.assign((size_t)z, 0); ok = T.d2h(e.data(), s->d_buf[1], (size_t)z); }
+            }
+            ok = ok && z0 == z1 && e0 == e1;
+            if (ok && z0 > 0) {
+                for (int v : {3, kNewLzp}) {
+                    s->lzp_default = v;
+                    s32& w = (v == 3) ? w0 : w1;
+                    double& td = (v == 3) ? td0 : td1;
+                    std::vector<u8>& d = (v == 3) ? d0 : d1;
+                    for (int rep = 0; rep < 2 && ok; rep++) {
+                        ok = T.h2d(e0.data(), s->d_buf[1], (size_t)z0);
+                        const double t0 = seconds_now();
+                        ok = ok && run_lzp_decode(s, s->d_buf[1], z0, s->d_buf[2], n + 32, &w) == cudaSuccess;
+                        td = std::min(td, seconds_now() - t0);
+                    }
+                    if (ok && w > 0) { d.assign((size_t)w, 0); ok = T.d2h(d.data(), s->d_buf[2], (size_t)w); }
+                }
+                ok = ok && w0 == n && w1 == n && d0 == d1 && memcmp(d0.data(), y.data(), (size_t)n) == 0;
+                // truncated token stream: same verdict
+                s32 c0 = -2, c1 = -2;
+                s->lzp_default = 3;
+                ok = ok && T.h2d(e0.data(), s->d_buf[1], (size_t)z0) && run_lzp_decode(s, s->d_buf[1], z0 / 2, s->d_buf[2], n + 32, &c0) == cudaSuccess;
+                s->lzp_default = kNewLzp;
+                ok = ok && T.h2d(e0.data(), s->d_buf[1], (size_t)z0) && run_lzp_decode(s, s->d_buf[1], z0 / 2, s->d_buf[2], n + 32, &c1) == cudaSuccess;
+                ok = ok && c0 == c1;
+            } else {
+                ok = false;
+            }
+            if (ok && (force || te1 + td1 < 0.9 * (te0 + td0))) c.lzp = kNewLzp;
+        }
+        cudaStreamSynchronize(s->stream);
+        s->launches = 0;
+    }
+    g_choice = c;
+    if (getenv("BZ3_B200_VERBOSE"))
+        fprintf(stderr, "[bz3_b200] kernels in effect: entropy encoder %d, decoder %d, LZP %d\n", c.cm_enc, c.cm_dec, c.lzp);
+}
+
+void apply_default_kernels(bz3_state* s) {
+    s->cm_enc = g_choice.cm_enc;
+    s->cm_dec = g_choice.cm_dec;
+    s->lzp_default = g_choice.lzp;
+}
+
+}  // namespace
+
 BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return nullptr;  // :536
     int dev = 0;
@@ -507,8 +689,9 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     s->block_size = block_size;
     s->device = dev;
     s->last_error = BZ3_OK;
-    s->cm_enc = env_int("BZ3_B200_CM_ENC", kCmEncDefault);
-    s->cm_dec = env_int("BZ3_B200_CM_DEC", kCmDecDefault);
+    s->cm_enc = 0;
+    s->cm_dec = 0;
+    s->lzp_default = 3;
     const size_t n = block_bound((size_t)block_size) + 64;
     s->cap = align_up(n + 256);
     bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -537,6 +720,8 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
         bz3_free(s);
         return nullptr;
     }
+    std::call_once(g_choice_once, kernel_autoselect, s);
+    apply_default_kernels(s);
     return s;
 }
 
@@ -872,6 +1057,7 @@ extern "C" BZIP3_API void bz3_b200_debug_cm_profile(unsigned long long* out16) {
 BZIP3_API int bz3_b200_get_variant(struct bz3_state* s, int stage) {
     if (stage == BZ3_STAGE_CM + 100) return s->cm_enc;
     if (stage == BZ3_STAGE_CM + 200) return s->cm_dec;
+    if (stage == BZ3_STAGE_LZP) return s->variant[stage] ? s->variant[stage] : s->lzp_default;
     return (stage >= 0 && stage < BZ3_STAGE_COUNT) ? s->variant[stage] : -1;
 }
 BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant) {
@@ -879,8 +1065,8 @@ BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant)
     // the entropy stage has separate encoder / decoder selections: BZ3_STAGE_CM sets both (0 = defaults),
     // BZ3_STAGE_CM + 100 the encoder alone, BZ3_STAGE_CM + 200 the decoder alone
     if (stage == BZ3_STAGE_CM) {
-        s->cm_enc = variant ? variant : env_int("BZ3_B200_CM_ENC", kCmEncDefault);
-        s->cm_dec = variant ? variant : env_int("BZ3_B200_CM_DEC", kCmDecDefault);
+        s->cm_enc = variant ? variant : g_choice.cm_enc;
+        s->cm_dec = variant ? variant : g_choice.cm_dec;
     } else if (stage == BZ3_STAGE_CM + 100) {
         s->cm_enc = variant;
     } else if (stage == BZ3_STAGE_CM + 200) {

@@ -59,10 +59,10 @@ BZIP3_API int32_t bz3_b200_stage_unbwt(struct bz3_state *state, const uint8_t *i
 BZIP3_API int32_t bz3_b200_stage_cm_encode(struct bz3_state *state, const uint8_t *in, int32_t n, uint8_t *out);
 BZIP3_API int bz3_b200_stage_cm_decode(struct bz3_state *state, const uint8_t *in, int32_t insize, uint8_t *out,
                                        int32_t n);
-/* implementation selectors for stages that have more than one kernel form (0 = the default).  The entropy
- * stage selects encoder and decoder kernels separately: stage BZ3_STAGE_CM sets both (0 = the defaults, which
- * the environment variables BZ3_B200_CM_ENC / BZ3_B200_CM_DEC may override), BZ3_STAGE_CM + 100 the encoder,
- * BZ3_STAGE_CM + 200 the decoder.  get_variant reports the selection in effect. */
+/* implementation selectors for stages that have more than one kernel form (0 = the default in effect: what the
+ * self-test of the first bz3_new() of the process chose, or what BZ3_B200_CM_ENC / BZ3_B200_CM_DEC / BZ3_B200_LZP
+ * pin).  The entropy stage selects encoder and decoder kernels separately: stage BZ3_STAGE_CM sets both,
+ * BZ3_STAGE_CM + 100 the encoder, BZ3_STAGE_CM + 200 the decoder.  get_variant reports the selection in effect. */
 BZIP3_API void bz3_b200_set_variant(struct bz3_state *state, int stage, int variant);
 BZIP3_API int bz3_b200_get_variant(struct bz3_state *state, int stage);
 

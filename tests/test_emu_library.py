@@ -72,7 +72,7 @@ def test_block_roundtrip_vs_oracle(st, name, data):
         assert st.last_error == 0
 
 
-@pytest.mark.parametrize("enc_v,dec_v,lzp_v", [(4, 4, 0), (6, 9, 2), (6, 5, 2), (0, 8, 2)])
+@pytest.mark.parametrize("enc_v,dec_v,lzp_v", [(4, 4, 3), (6, 9, 2), (6, 5, 2), (0, 8, 2)])
 def test_block_roundtrip_with_other_kernels(st, enc_v, dec_v, lzp_v):
     """The opt-in entropy / LZP kernels selected through the block API give the same bytes."""
     L = st.L
@@ -166,3 +166,34 @@ def test_frame_api_and_helpers(emulib):
         assert osz_r.value == osz.value and bytes(out_r[:osz_r.value]) == bytes(frame)
     assert L.bz3_bound(1000) == 1000 + 1000 // 50 + 32
     assert not L.bz3_new(1000) and not L.bz3_new((511 << 20) + 1)   # block size out of range
+
+
+def test_default_kernels_come_from_the_self_test(emulib):
+    """bz3_new runs the on-device self-test once per process (kernel_autoselect in bz3_api.cu): the newer kernels
+    become the defaults only if they reproduce the proven kernels' bytes and are faster.  Here (emulator, where they
+    are slower) the proven ones must stay; with BZ3_B200_AUTOSELECT=force a fresh process must select the newer
+    ones -- which proves that every comparison of the self-test passes -- and still code blocks bit-exactly."""
+    import subprocess
+    import sys
+    with bzip3_b200.Bz3State(BS) as s:
+        got = (emulib.bz3_b200_get_variant(s.handle, 105), emulib.bz3_b200_get_variant(s.handle, 205),
+               emulib.bz3_b200_get_variant(s.handle, 3))
+    assert got in ((0, 0, 3), (6, 8, 2), (6, 0, 3), (0, 8, 3), (0, 0, 2), (6, 8, 3), (6, 0, 2), (0, 8, 2))
+    script = (
+        "import os, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import bzip3_b200\n"
+        "from bzip3_b200 import synth\n"
+        "from tests import refs\n"
+        "data = synth.zipf_text(1500, seed=2).tobytes()\n"
+        "with bzip3_b200.Bz3State(%d) as s:\n"
+        "    L = s.L\n"
+        "    print('CHOICE', L.bz3_b200_get_variant(s.handle, 105), L.bz3_b200_get_variant(s.handle, 205), L.bz3_b200_get_variant(s.handle, 3))\n"
+        "    enc, r = s.encode_block(data)\n"
+        "    want = refs.oracle_encode_block(data, %d)\n"
+        "    dec, r2 = s.decode_block(enc, len(data))\n"
+        "    print('EXACT', r == want[1] and enc == want[0] and dec == data)\n" % (ROOT, BS, BS))
+    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="force")
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert "CHOICE 6 8 2" in out.stdout, out.stdout + out.stderr
+    assert "EXACT True" in out.stdout, out.stdout + out.stderr

@@ -86,7 +86,7 @@ def test_stage_rle(st, O, name, data):
         assert bytes(dg[:n]) == bytes(dw[:n]), (cut, first_diff(dg[:n], dw[:n]))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["warp", "single", "warp_windows_in_flight"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["default_in_effect", "single", "windows_in_flight_bulk", "one_window"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_stage_lzp(st, O, name, data, variant):
     if variant == 2 and not NEW_UNTIMED:

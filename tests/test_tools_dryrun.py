@@ -41,6 +41,9 @@ class FakeLib:
         elif stage == 3:
             self.lzp = v
 
+    def bz3_b200_get_variant(self, h, stage):
+        return {105: self.enc, 205: self.dec, 3: self.lzp}.get(stage, 0)
+
     def bz3_b200_stage_bwt(self, h, pin, n, pout):
         return self.O.orc_bwt(pin, pout, n)
 
@@ -101,6 +104,6 @@ def test_eval_variants_script_logic(tmp_path, monkeypatch, capsys):
     # every variant the script announces was really selected for its calls
     assert {v for k, v in fake.calls if k == "enc"} == set(mod.ENC_VARIANTS)
     assert {v for k, v in fake.calls if k == "dec"} >= set(mod.DEC_VARIANTS) - {3}
-    assert {v for k, v in fake.calls if k.startswith("lzp")} == {0, 2}
+    assert {v for k, v in fake.calls if k.startswith("lzp")} == {3, 2}
     for name, rec in res["sets"].items():
         assert all(d["ok"] for d in rec["enc"].values()) and all(d["ok"] for d in rec["dec"].values()), name

@@ -47,6 +47,13 @@ def main():
             ("mixed", synth.mixed(n, seed=4244, segment=max(n // 4, 1 << 16)))]
     result = {"n": n, "sets": {}, "ok": True}
     with bzip3_b200.Bz3State(max(n, 1 << 20)) as st:
+        try:   # what the self-test of the library chose for this process
+            result["defaults_in_effect"] = {"cm_enc": L.bz3_b200_get_variant(st.handle, CM + 100),
+                                            "cm_dec": L.bz3_b200_get_variant(st.handle, CM + 200),
+                                            "lzp": L.bz3_b200_get_variant(st.handle, 3)}
+            print("defaults in effect:", result["defaults_in_effect"], flush=True)
+        except Exception:
+            pass
         prep = {}
         for name, data in sets:
             data = np.ascontiguousarray(data[:n])
@@ -103,7 +110,7 @@ def main():
                     (ENC_VARIANTS if kind == "enc" else DEC_VARIANTS)[v]), flush=True)
                 with open(args.out, "w") as f:
                     json.dump(result, f, indent=1)
-        # LZP pre-pass: one-window kernels (default) against variant 2 (windows in flight / bulk decoder)
+        # LZP pre-pass: one-window kernels (variant 3) against variant 2 (windows in flight / bulk decoder)
         LZP = 3  # BZ3_STAGE_LZP
         lzp_sets = sets + [("log", synth.log_stream(n, seed=4245))]
         result["lzp"] = {}
@@ -116,7 +123,7 @@ def main():
             want = np.zeros(n + 64, np.uint8)
             rw = O.orc_lzp_encode(pad.ctypes.data_as(u8p), n, want.ctypes.data_as(u8p), lp)
             rec = {"lzp_size": int(rw)}
-            for v in (0, 2):
+            for v in (3, 2):   # 3 = one window per step (round-1 kernels), 2 = windows in flight / bulk decoder
                 L.bz3_b200_set_variant(st.handle, LZP, v)
                 got = np.zeros(n + 64, np.uint8)
                 t0 = time.perf_counter()
