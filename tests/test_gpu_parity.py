@@ -332,3 +332,22 @@ def test_reference_cross_decode_when_available():
         enc_ref = refs.api_encode_block(R, data, 1 << 20)[0]
         assert enc_ref == enc
         assert s.decode_block(enc_ref, len(data))[0] == data
+
+
+def test_default_kernels_in_effect(st, capsys):
+    """Which kernels the self-test of bz3_new chose on this machine.  Whatever it chose, the block
+    tests above ran with it; a fresh process with BZ3_B200_AUTOSELECT=0 must keep the round-1 kernels."""
+    import subprocess
+    import sys
+    L = st.L
+    choice = (L.bz3_b200_get_variant(st.handle, 105), L.bz3_b200_get_variant(st.handle, 205), L.bz3_b200_get_variant(st.handle, 3))
+    with capsys.disabled():
+        print("\n[bz3_b200] kernels in effect (entropy encoder, decoder, LZP): %s" % (choice,))
+    assert choice[0] in (0, 6) and choice[1] in (0, 8) and choice[2] in (3, 2)
+    code = ("import bzip3_b200\n"
+            "with bzip3_b200.Bz3State(1 << 20) as s:\n"
+            "    print('CHOICE', s.L.bz3_b200_get_variant(s.handle, 105), s.L.bz3_b200_get_variant(s.handle, 205), "
+            "s.L.bz3_b200_get_variant(s.handle, 3))\n")
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BZ3_B200_AUTOSELECT="0"), cwd=refs.ROOT,
+                         capture_output=True, text=True, timeout=300)
+    assert "CHOICE 0 0 3" in out.stdout, out.stdout + out.stderr
