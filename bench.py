@@ -244,6 +244,7 @@ def run_b200_arm(args, rank, world, local_rank):
     states = [bzip3_b200.Bz3State(bs) for _ in blocks]
     hs = (C.c_void_p * nb)(*[s.handle for s in states])
     cm_variants = (L.bz3_b200_get_variant(states[0].handle, 5 + 100), L.bz3_b200_get_variant(states[0].handle, 5 + 200))
+    lzp_variant = L.bz3_b200_get_variant(states[0].handle, 3)
     sizes = (C.c_int32 * nb)(*[len(b) for b in blocks])
     osz = (C.c_int32 * nb)(*[len(b) for b in blocks])
     enc_sizes = (C.c_int32 * nb)()
@@ -423,6 +424,9 @@ def run_b200_arm(args, rank, world, local_rank):
             "config": {"workload": args.workload, "description": w["desc"], "block_size": bs, "blocks_per_gpu": nb,
                        "bytes_per_gpu": total, "parallelism": f"blocks sharded {world} way(s), one stream per block",
                        "l2": "256 MiB flush buffer written before every timed step; per-block arenas >> 126 MB L2",
+                       "kernels_in_effect": {"entropy_encoder": int(cm_variants[0]), "entropy_decoder": int(cm_variants[1]),
+                                             "lzp": int(lzp_variant),
+                                             "how": "on-device self-test at the first bz3_new (DESIGN.md 6c); 0/0/3 = round-1 kernels"},
                        "definition": "one step = encode + decode of every block; value = bytes / step time"},
             "encode_MiB_per_s": round(job_bytes / MIB / (sum_enc / args.steps / 1e3), 3),
             "decode_MiB_per_s": round(job_bytes / MIB / (sum_dec / args.steps / 1e3), 3),
