@@ -8,19 +8,20 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbzip3_b200.so")
+HELPER = os.path.join(HERE, "bz3_selftest")   # spawned by the library for the self-test behind the default kernels
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
          "-fPIC,-fvisibility=hidden", "-shared"]
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + [
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp"))) + [
         os.path.join(os.path.dirname(HERE), "include", "libbz3.h"),
         os.path.join(os.path.dirname(HERE), "include", "bz3_b200.h")]
 
 
 def stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(HELPER):
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(s) > t for s in sources())
@@ -36,6 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libbzip3_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-O2", "-o", HELPER, os.path.join(CSRC, "selftest_helper.cpp"), "-ldl"])
     return LIB
 
 

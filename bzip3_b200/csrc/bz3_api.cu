@@ -6,10 +6,21 @@
 // bz3_encode_blocks / bz3_decode_blocks (:813-872) with one host thread + one CUDA stream per block.
 #include <algorithm>
 #include <chrono>
+#if !defined(BZ_EMU) || defined(BZ_EMU_SPAWN_TEST)
+#define BZ_SELFTEST_SPAWN 1
+#include <dlfcn.h>
+#include <poll.h>
+#include <signal.h>
+#include <spawn.h>
+#include <sys/wait.h>
+#include <unistd.h>
+extern char** environ;
+#endif
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -570,16 +581,14 @@ struct SelfTest {
     }
 };
 
-void kernel_autoselect(bz3_state* s) {
-    KernelChoice c;   // the proven kernels
-    const char* mode = getenv("BZ3_B200_AUTOSELECT");
-    const bool off = mode && mode[0] == '0';
-    const bool force = mode && mode[0] == 'f';
-    const bool pin_enc = env_set("BZ3_B200_CM_ENC"), pin_dec = env_set("BZ3_B200_CM_DEC"), pin_lzp = env_set("BZ3_B200_LZP");
-    if (pin_enc) c.cm_enc = env_int("BZ3_B200_CM_ENC", 0);
-    if (pin_dec) c.cm_dec = env_int("BZ3_B200_CM_DEC", 0);
-    if (pin_lzp) c.lzp = env_int("BZ3_B200_LZP", 3);
-    if (!off) {
+struct Pins {
+    bool enc, dec, lzp;
+};
+
+// The device part of the self-test: returns the kernels to use, starting from `c` (proven kernels + pins).
+KernelChoice selftest_on_device(bz3_state* s, KernelChoice c, const bool force, const Pins pin) {
+    const bool pin_enc = pin.enc, pin_dec = pin.dec, pin_lzp = pin.lzp;
+    {
 #if defined(BZ_EMU)
         const s32 n = 3000;    // the CPU emulator codes a few kilobytes per second
 #else
@@ -663,9 +672,105 @@ void kernel_autoselect(bz3_state* s) {
         cudaStreamSynchronize(s->stream);
         s->launches = 0;
     }
+    return c;
+}
+
+bool g_selftest_child = false;   // this process IS the helper: test in process
+
+#if defined(BZ_SELFTEST_SPAWN)
+// The candidates have to prove themselves in ANOTHER process first: bzip3_b200/bz3_selftest (a few lines, see
+// selftest_helper.cpp) loads this library, runs selftest_on_device on the same device and prints the choice.  If a
+// candidate kernel hung or crashed there, the helper is killed after a deadline and this process -- whose CUDA
+// context never saw that kernel -- simply keeps the proven kernels.
+bool selftest_in_child(int device, KernelChoice& c) {
+    Dl_info info;
+    if (!dladdr(reinterpret_cast<void*>(&bz3_bound), &info) || !info.dli_fname) return false;
+    std::string lib = info.dli_fname;
+    const size_t slash = lib.rfind('/');
+    std::string helper = (slash == std::string::npos ? std::string(".") : lib.substr(0, slash)) + "/bz3_selftest";
+    if (access(helper.c_str(), X_OK) != 0) return false;
+    int fd[2];
+    if (pipe(fd) != 0) return false;
+    posix_spawn_file_actions_t fa;
+    posix_spawn_file_actions_init(&fa);
+    posix_spawn_file_actions_adddup2(&fa, fd[1], 1);
+    posix_spawn_file_actions_addclose(&fa, fd[0]);
+    posix_spawn_file_actions_addclose(&fa, fd[1]);
+    char dev[16];
+    snprintf(dev, sizeof dev, "%d", device);
+    char* argv[] = {const_cast<char*>(helper.c_str()), const_cast<char*>(lib.c_str()), dev, nullptr};
+    pid_t pid = 0;
+    const int rc = posix_spawn(&pid, helper.c_str(), &fa, nullptr, argv, environ);
+    posix_spawn_file_actions_destroy(&fa);
+    close(fd[1]);
+    if (rc != 0) { close(fd[0]); return false; }
+    std::string out;
+    // a fresh box pages the driver in slowly; a hung kernel never ends (BZ3_B200_SELFTEST_TIMEOUT: seconds, for tests)
+    const double deadline = seconds_now() + (double)std::max(1, env_int("BZ3_B200_SELFTEST_TIMEOUT", 90));
+    bool eof = false;
+    while (!eof) {
+        const double left = deadline - seconds_now();
+        if (left <= 0) break;
+        struct pollfd pf = {fd[0], POLLIN, 0};
+        const int pr = poll(&pf, 1, (int)(left * 1000.0) + 1);
+        if (pr < 0) break;
+        if (pr == 0) continue;
+        char buf[256];
+        const ssize_t got = read(fd[0], buf, sizeof buf);
+        if (got <= 0) eof = true; else out.append(buf, (size_t)got);
+    }
+    close(fd[0]);
+    int status = 0;
+    if (!eof) kill(pid, SIGKILL);
+    waitpid(pid, &status, 0);
+    if (!eof || !WIFEXITED(status) || WEXITSTATUS(status) != 0) return false;
+    int e = -1, d = -1, l = -1;
+    const size_t at = out.find("BZ3SELFTEST");
+    if (at == std::string::npos || sscanf(out.c_str() + at, "BZ3SELFTEST %d %d %d", &e, &d, &l) != 3) return false;
+    if ((e != 0 && e != 6) || (d != 0 && d != 8) || (l != 3 && l != 2)) return false;
+    c.cm_enc = e;
+    c.cm_dec = d;
+    c.lzp = l;
+    return true;
+}
+#endif
+
+void kernel_autoselect(bz3_state* s) {
+    KernelChoice c;   // the proven kernels
+    const char* mode = getenv("BZ3_B200_AUTOSELECT");
+    const bool off = mode && mode[0] == '0';
+    const bool force = mode && mode[0] == 'f';
+    const Pins pin = {env_set("BZ3_B200_CM_ENC"), env_set("BZ3_B200_CM_DEC"), env_set("BZ3_B200_LZP")};
+    if (pin.enc) c.cm_enc = env_int("BZ3_B200_CM_ENC", 0);
+    if (pin.dec) c.cm_dec = env_int("BZ3_B200_CM_DEC", 0);
+    if (pin.lzp) c.lzp = env_int("BZ3_B200_LZP", 3);
+    const char* how = "round-1 kernels (self-test off)";
+    if (!off && !(pin.enc && pin.dec && pin.lzp)) {
+#if defined(BZ_SELFTEST_SPAWN)
+        const bool in_process = g_selftest_child || force || (mode && mode[0] == 'i');
+#else
+        const bool in_process = true;   // plain emulator build: no helper
+#endif
+        if (in_process) {
+            c = selftest_on_device(s, c, force, pin);
+            how = "self-test in this process";
+        } else {
+#if defined(BZ_SELFTEST_SPAWN)
+            KernelChoice from_child = c;
+            if (selftest_in_child(s->device, from_child)) {
+                if (!pin.enc) c.cm_enc = from_child.cm_enc;
+                if (!pin.dec) c.cm_dec = from_child.cm_dec;
+                if (!pin.lzp) c.lzp = from_child.lzp;
+                how = "self-test in the helper process";
+            } else {
+                how = "round-1 kernels (the self-test helper was not available or did not finish)";
+            }
+#endif
+        }
+    }
     g_choice = c;
     if (getenv("BZ3_B200_VERBOSE"))
-        fprintf(stderr, "[bz3_b200] kernels in effect: entropy encoder %d, decoder %d, LZP %d\n", c.cm_enc, c.cm_dec, c.lzp);
+        fprintf(stderr, "[bz3_b200] kernels in effect: entropy encoder %d, decoder %d, LZP %d -- %s\n", c.cm_enc, c.cm_dec, c.lzp, how);
 }
 
 void apply_default_kernels(bz3_state* s) {
@@ -1054,6 +1159,18 @@ extern "C" BZIP3_API void bz3_b200_debug_cm_profile(unsigned long long* out16) {
     cudaMemcpyFromSymbol(out16, g_cm_prof, sizeof(unsigned long long) * 48);
 }
 #endif
+// What the self-test chooses on `device`, computed in THIS process (entry point of bzip3_b200/bz3_selftest).
+BZIP3_API int bz3_b200_selftest(int device, int* cm_enc, int* cm_dec, int* lzp) {
+    g_selftest_child = true;
+    if (cudaSetDevice(device) != cudaSuccess) return 2;
+    bz3_state* s = bz3_new(65 * 1024);
+    if (!s) return 3;
+    *cm_enc = g_choice.cm_enc;
+    *cm_dec = g_choice.cm_dec;
+    *lzp = g_choice.lzp;
+    bz3_free(s);
+    return 0;
+}
 BZIP3_API int bz3_b200_get_variant(struct bz3_state* s, int stage) {
     if (stage == BZ3_STAGE_CM + 100) return s->cm_enc;
     if (stage == BZ3_STAGE_CM + 200) return s->cm_dec;

@@ -65,6 +65,10 @@ BZIP3_API int bz3_b200_stage_cm_decode(struct bz3_state *state, const uint8_t *i
  * BZ3_STAGE_CM + 100 the encoder, BZ3_STAGE_CM + 200 the decoder.  get_variant reports the selection in effect. */
 BZIP3_API void bz3_b200_set_variant(struct bz3_state *state, int stage, int variant);
 BZIP3_API int bz3_b200_get_variant(struct bz3_state *state, int stage);
+/* the self-test behind the defaults, run in the calling process on `device` (used by the helper bz3_selftest, which the
+ * library spawns so that a misbehaving candidate kernel can never take the caller's CUDA context down); returns 0 and
+ * the kernels it would choose */
+BZIP3_API int bz3_b200_selftest(int device, int *cm_enc, int *cm_dec, int *lzp);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,18 @@
 #include <map>
 #include <vector>
 #include <sys/mman.h>
+// system headers that product code includes later must come before the CUDA vocabulary macros below (__noinline__ ...)
+#include <dlfcn.h>
+#include <poll.h>
+#include <signal.h>
+#include <spawn.h>
+#include <sys/wait.h>
+#include <unistd.h>
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <string>
+#include <thread>
 
 // ThreadSanitizer build (tools/emu_tsan.py): every CUDA thread is announced to TSan as a fiber and every barrier /
 // warp collective as a release-acquire edge, so a shared- or global-memory access pair of two CUDA threads with no
