@@ -594,7 +594,7 @@ KernelChoice selftest_on_device(bz3_state* s, KernelChoice c, const bool force, 
 #else
         const s32 n = 48 * 1024;
 #endif
-        constexpr int kNewEnc = 6, kNewDec = 8, kNewLzp = 2;
+        constexpr int kNewEnc = 6, kNewLzp = 2;
         SelfTest T{s};
         std::vector<u8> x((size_t)n + 64, 0), ref, cand, back;
         selftest_bytes(x.data(), n, 20260923u);
@@ -609,14 +609,21 @@ KernelChoice selftest_on_device(bz3_state* s, KernelChoice c, const bool force, 
             T.h2d(ref.data(), s->d_buf[1], (size_t)r0);   // the decoders below read the proven encoder's stream
         }
         if (base_ok && !pin_dec) {
-            std::vector<u8> full0, full1, cut0, cut1;
-            double t0d = 0, t1d = 0, tt = 0;
-            bool ok = T.cm_decode(0, r0, n, full0, t0d) && T.cm_decode(kNewDec, r0, n, full1, t1d) && full0 == full1 &&
-                      memcmp(full1.data(), x.data(), (size_t)n) == 0;
-            // truncated stream: the decoders must agree on the garbage as well (read_in() past the end, src/libbz3.c:345)
-            ok = ok && T.cm_decode(0, r0 / 2, n, cut0, tt) && T.cm_decode(kNewDec, r0 / 2, n, cut1, tt) && cut0 == cut1;
-            ok = ok && T.cm_decode(0, 5, n, cut0, tt) && T.cm_decode(kNewDec, 5, n, cut1, tt) && cut0 == cut1;
-            if (ok && (force || t1d < 0.9 * t0d)) c.cm_dec = kNewDec;
+            std::vector<u8> full0, cut0a, cut0b, full1, cut1;
+            double t0d = 0, tt = 0;
+            // truncated streams: the decoders must agree on the garbage as well (read_in() past the end, src/libbz3.c:345)
+            bool ok0 = T.cm_decode(0, r0 / 2, n, cut0a, tt) && T.cm_decode(0, 5, n, cut0b, tt) && T.cm_decode(0, r0, n, full0, t0d) &&
+                       memcmp(full0.data(), x.data(), (size_t)n) == 0;
+            double best = 0.9 * t0d;
+            for (int v : {8, 9}) {   // walker kernels: slim model threads / branch-light model threads
+                double t1d = 0;
+                bool ok = ok0 && T.cm_decode(v, r0 / 2, n, cut1, tt) && cut1 == cut0a && T.cm_decode(v, 5, n, cut1, tt) && cut1 == cut0b &&
+                          T.cm_decode(v, r0, n, full1, t1d) && full1 == full0;
+                if (ok && (t1d < best || (force && c.cm_dec == 0))) {
+                    c.cm_dec = v;
+                    best = std::min(best, t1d);
+                }
+            }
         }
         // ---- LZP: an input with long matches, escapes and literal stretches
         if (!pin_lzp) {
@@ -727,7 +734,7 @@ bool selftest_in_child(int device, KernelChoice& c) {
     int e = -1, d = -1, l = -1;
     const size_t at = out.find("BZ3SELFTEST");
     if (at == std::string::npos || sscanf(out.c_str() + at, "BZ3SELFTEST %d %d %d", &e, &d, &l) != 3) return false;
-    if ((e != 0 && e != 6) || (d != 0 && d != 8) || (l != 3 && l != 2)) return false;
+    if ((e != 0 && e != 6) || (d != 0 && d != 8 && d != 9) || (l != 3 && l != 2)) return false;
     c.cm_enc = e;
     c.cm_dec = d;
     c.lzp = l;

@@ -178,7 +178,7 @@ def test_default_kernels_come_from_the_self_test(emulib):
     with bzip3_b200.Bz3State(BS) as s:
         got = (emulib.bz3_b200_get_variant(s.handle, 105), emulib.bz3_b200_get_variant(s.handle, 205),
                emulib.bz3_b200_get_variant(s.handle, 3))
-    assert got in ((0, 0, 3), (6, 8, 2), (6, 0, 3), (0, 8, 3), (0, 0, 2), (6, 8, 3), (6, 0, 2), (0, 8, 2))
+    assert got[0] in (0, 6) and got[1] in (0, 8, 9) and got[2] in (3, 2)
     script = (
         "import os, sys\n"
         "sys.path.insert(0, %r)\n"
@@ -195,5 +195,5 @@ def test_default_kernels_come_from_the_self_test(emulib):
         "    print('EXACT', r == want[1] and enc == want[0] and dec == data)\n" % (ROOT, BS, BS))
     env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="force")
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
-    assert "CHOICE 6 8 2" in out.stdout, out.stdout + out.stderr
+    assert "CHOICE 6 8 2" in out.stdout or "CHOICE 6 9 2" in out.stdout, out.stdout + out.stderr
     assert "EXACT True" in out.stdout, out.stdout + out.stderr

@@ -77,12 +77,12 @@ def test_choice_comes_from_the_helper_process(spawn_dir):
     direct = subprocess.run([HELPER, SO, "0"], capture_output=True, text=True, timeout=600)
     assert direct.returncode == 0 and direct.stdout.startswith("BZ3SELFTEST ")
     e, d, l = direct.stdout.split()[1:4]
-    assert e in ("0", "6") and d in ("0", "8") and l in ("3", "2")
+    assert e in ("0", "6") and d in ("0", "8", "9") and l in ("3", "2")
 
 
 @pytest.mark.parametrize("name,helper,env", [
     ("hangs", "#!/bin/sh\nexec sleep 100\n", {"BZ3_B200_SELFTEST_TIMEOUT": "2"}),
-    ("nonsense", "#!/bin/sh\necho BZ3SELFTEST 6 9 2\n", {}),
+    ("nonsense", "#!/bin/sh\necho BZ3SELFTEST 6 5 2\n", {}),
     ("crashes", "#!/bin/sh\nkill -SEGV $$\n", {}),
     ("silent", "#!/bin/sh\nexit 0\n", {}),
     ("missing", "", {}),
