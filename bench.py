@@ -54,6 +54,10 @@ WORKLOADS = {
                        desc="1 GiB synthetic source corpus, -b 256 (4 blocks)"),
     "src256m_b64": dict(gen="source_corpus", nbytes=256 << 20, block=64 << 20, seed=synth.SEED_SOURCE,
                         desc="256 MiB synthetic source corpus, -b 64 (4 blocks)"),
+    # not a BASELINE config: many blocks per GPU, to measure what blocks in flight buy (the per-device
+    # workspace pool lets a B200 hold far more blocks than it has SMs); 128 blocks = 128 single-CTA coder kernels at once
+    "zipf2g_b16": dict(gen="zipf_text", nbytes=2 << 30, block=16 << 20, seed=synth.SEED_ZIPF_TEXT,
+                       desc="2 GiB synthetic Zipf(1.1) text, -b 16 (128 blocks in flight per GPU)"),
     "zipf8m_b1": dict(gen="zipf_text", nbytes=8 << 20, block=1 << 20, seed=synth.SEED_ZIPF_TEXT,
                       desc="8 MiB synthetic Zipf text, -b 1 (8 blocks) -- quick self-test"),
 }
@@ -423,10 +427,12 @@ def run_b200_arm(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "description": w["desc"], "block_size": bs, "blocks_per_gpu": nb,
                        "bytes_per_gpu": total, "parallelism": f"blocks sharded {world} way(s), one stream per block",
-                       "l2": "256 MiB flush buffer written before every timed step; per-block arenas >> 126 MB L2",
+                       "l2": "256 MiB flush buffer written before every timed step; block buffers + shared stage workspaces >> 126 MB L2",
                        "kernels_in_effect": {"entropy_encoder": int(cm_variants[0]), "entropy_decoder": int(cm_variants[1]),
                                              "lzp": int(lzp_variant),
                                              "how": "on-device self-test at the first bz3_new (DESIGN.md 6c); 0/0/3 = round-1 kernels"},
+                       "hbm_bytes": {"per_block_state": int(L.bz3_b200_device_bytes(states[0].handle)),
+                                     "shared_stage_workspaces": int(L.bz3_b200_workspace_bytes(states[0].handle))},
                        "definition": "one step = encode + decode of every block; value = bytes / step time"},
             "encode_MiB_per_s": round(job_bytes / MIB / (sum_enc / args.steps / 1e3), 3),
             "decode_MiB_per_s": round(job_bytes / MIB / (sum_dec / args.steps / 1e3), 3),

@@ -83,6 +83,8 @@ def lib():
     L.bz3_b200_state_device.argtypes = [C.c_void_p]
     L.bz3_b200_device_bytes.restype = C.c_size_t
     L.bz3_b200_device_bytes.argtypes = [C.c_void_p]
+    L.bz3_b200_workspace_bytes.restype = C.c_size_t
+    L.bz3_b200_workspace_bytes.argtypes = [C.c_void_p]
     L.bz3_b200_upload.restype = C.c_int
     L.bz3_b200_upload.argtypes = [C.c_void_p, _u8p, C.c_int32]
     L.bz3_b200_download.restype = C.c_int

@@ -6,6 +6,7 @@
 // bz3_encode_blocks / bz3_decode_blocks (:813-872) with one host thread + one CUDA stream per block.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #if !defined(BZ_EMU) || defined(BZ_EMU_SPAWN_TEST)
 #define BZ_SELFTEST_SPAWN 1
 #include <dlfcn.h>
@@ -83,7 +84,9 @@ struct bz3_state {
     s32* d_lut;         // LZP table
     u32* d_scal;        // device scalars
     u32* h_scal;        // pinned mirror (1024 u32)
-    Arena arena;        // stage workspace
+    Arena arena;        // stage workspace: a lease from the device's pool, valid inside one stage call (ArenaLease)
+    size_t arena_need;  // workspace bytes the largest stage of this state needs
+    bool pool_attached;
     size_t device_bytes;
     // data staged by bz3_b200_upload / produced by *_resident
     int resident_buf;   // index of the buffer holding resident data
@@ -103,6 +106,149 @@ struct bz3_state {
 
 namespace {
 
+int env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : fallback;
+}
+bool env_set(const char* name) {
+    const char* v = getenv(name);
+    return v && *v;
+}
+
+// ------------------------------------------------------------------------------- stage workspace pool
+// mRLE, the suffix sort and the inverse BWT need a workspace of up to 48 bytes per input byte (12.9 GB for a 256 MiB
+// block, 25.7 GB at 511 MiB) for the fraction of a second a block spends in them, while the entropy stage then holds
+// the block for seconds on ONE thread block.  Throughput on a B200 is blocks in flight, so the workspace must not be a
+// per-state cost: the states of a device share kArenaSlots workspaces (BZ3_B200_ARENAS, default 2: one block sorts
+// while the next one's launches are queued), leased for the duration of one stage call.  What a state owns is its
+// three data buffers and the LZP table: ~3.06 bytes per byte of block size instead of ~51, i.e. >150 blocks of
+// 256 MiB resident in the 180 GB of one B200 instead of 13.
+constexpr int kMaxDevices = 64;
+constexpr int kMaxArenaSlots = 8;
+
+struct ArenaPool {
+    std::mutex m;
+    std::condition_variable cv;
+    struct Slot {
+        u8* base = nullptr;
+        size_t size = 0;
+        bool busy = false;
+    } slot[kMaxArenaSlots];
+    int nslots = 0;   // fixed at the first attach
+    int states = 0;   // live states of this device
+};
+ArenaPool g_pool[kMaxDevices];
+
+// Makes a free slot at least `need` bytes large (caller holds the pool's mutex).  The new workspace is allocated before
+// the old one is released when both fit; if neither order works the old size is restored so that the states which
+// rely on it keep working.
+bool pool_grow_slot(ArenaPool::Slot& sl, size_t need) {
+    if (sl.size >= need) return true;
+    u8* fresh = nullptr;
+    if (cudaMalloc(&fresh, need) != cudaSuccess) {
+        cudaGetLastError();   // reported through the return value, not left behind as a sticky error
+        fresh = nullptr;
+        const size_t old = sl.size;
+        if (sl.base) cudaFree(sl.base);
+        sl.base = nullptr;
+        sl.size = 0;
+        if (cudaMalloc(&fresh, need) != cudaSuccess) {
+            cudaGetLastError();
+            if (old && cudaMalloc(&sl.base, old) == cudaSuccess) sl.size = old;
+            else { sl.base = nullptr; cudaGetLastError(); }
+            return false;
+        }
+    } else if (sl.base) {
+        cudaFree(sl.base);
+    }
+    sl.base = fresh;
+    sl.size = need;
+    return true;
+}
+
+// bz3_new: registers a state and sizes the workspaces for it, so that running out of device memory is reported where
+// the reference reports it (bz3_new returns NULL, src/libbz3.c:553-561) and never in the middle of a block.  Slot 0 is
+// always large enough for every live state; the further slots are sized from the second state on (a lone state
+// cannot use two) and are a bonus: failing to grow one of them is not an error.
+bool pool_attach(int dev, size_t need) {
+    ArenaPool& P = g_pool[dev];
+    std::unique_lock<std::mutex> lk(P.m);
+    if (P.nslots == 0) {
+        int k = env_int("BZ3_B200_ARENAS", 2);
+        P.nslots = k < 1 ? 1 : (k > kMaxArenaSlots ? kMaxArenaSlots : k);
+    }
+    const int want = std::min(P.nslots, P.states + 1);
+    for (int k = 0; k < want; k++) {
+        P.cv.wait(lk, [&] { return !P.slot[k].busy; });
+        if (!pool_grow_slot(P.slot[k], need) && k == 0) return false;
+    }
+    P.states++;
+    return true;
+}
+
+void pool_detach(int dev) {
+    ArenaPool& P = g_pool[dev];
+    std::unique_lock<std::mutex> lk(P.m);
+    if (--P.states > 0) return;
+    P.states = 0;
+    for (int k = 0; k < P.nslots; k++) {   // the last state of the device takes the workspaces with it
+        P.cv.wait(lk, [&] { return !P.slot[k].busy; });
+        if (P.slot[k].base) cudaFree(P.slot[k].base);
+        P.slot[k] = ArenaPool::Slot();
+    }
+    P.nslots = 0;
+}
+
+// One stage call's hold on a workspace.  The constructor waits for a free one; the destructor gives it back only when
+// the state's stream has drained, so no kernel of this stage can still be using it (every stage driver below has
+// synchronised by then on its good path; this covers the early returns).
+struct ArenaLease {
+    bz3_state* s;
+    int k = -1;
+    ArenaLease(bz3_state* st, int stage) : s(st) {
+        ArenaPool& P = g_pool[s->device];
+        {
+            std::unique_lock<std::mutex> lk(P.m);
+            bool any = false;
+            P.cv.wait(lk, [&] {   // a free workspace that is large enough for this state (slot 0 always is, see pool_attach)
+                any = false;
+                for (int i = 0; i < P.nslots; i++)
+                    if (P.slot[i].size >= s->arena_need) {
+                        any = true;
+                        if (!P.slot[i].busy) { k = i; return true; }
+                    }
+                return !any;
+            });
+            if (!any || k < 0) { k = -1; return; }   // only if a later bz3_new lost slot 0 while running out of memory
+            P.slot[k].busy = true;
+            s->arena.base = P.slot[k].base;
+            s->arena.size = P.slot[k].size;
+            s->arena.used = 0;
+        }
+        if (s->clk.a[stage]) cudaEventRecord(s->clk.a[stage], s->stream);   // the stage's clock starts once the workspace is there
+    }
+    ~ArenaLease() {
+        if (k < 0) return;
+        cudaStreamSynchronize(s->stream);
+        give_back();
+    }
+    bool ok() const { return k >= 0; }
+    ArenaLease(const ArenaLease&) = delete;
+    ArenaLease& operator=(const ArenaLease&) = delete;
+
+private:
+    void give_back() {
+        ArenaPool& P = g_pool[s->device];
+        s->arena = Arena();
+        {
+            std::lock_guard<std::mutex> lk(P.m);
+            P.slot[k].busy = false;
+        }
+        k = -1;
+        P.cv.notify_all();
+    }
+};
+
 size_t sufsort_arena_bytes(size_t n) {
     return align_up(4 * n) + align_up(4 * (n + 1)) + 2 * align_up(8 * n) + 6 * align_up(4 * n) +
            align_up(4 * sufsort_temp_elems((u32)n)) + 16 * kAlign;
@@ -114,7 +260,7 @@ size_t other_arena_bytes(size_t n) {
     return mr > ub ? mr : ub;
 }
 
-bool carve_sufsort(bz3_state* s, u32 n, SufsortBuffers& B) {
+bool carve_sufsort(bz3_state* s, u32 n, SufsortBuffers& B) {   // inside an ArenaLease
     Arena& A = s->arena;
     A.reset();
     B.sa = A.take<u32>(n);
@@ -171,6 +317,8 @@ cudaError_t run_crc(bz3_state* s, const u8* d_in, u32 n, u32* crc_out) {
 }
 
 cudaError_t run_rle_encode(bz3_state* s, const u8* d_in, u32 n, u8* d_out, s32* out_size) {
+    ArenaLease lease(s, BZ3_STAGE_RLE);
+    if (!lease.ok()) return cudaErrorMemoryAllocation;
     Arena& A = s->arena;
     A.reset();
     MrleScratch S;
@@ -185,6 +333,8 @@ cudaError_t run_rle_encode(bz3_state* s, const u8* d_in, u32 n, u8* d_out, s32* 
 }
 
 cudaError_t run_rle_decode(bz3_state* s, const u8* d_in, u32 maxin, u8* d_out, u32 outlen, int* err) {
+    ArenaLease lease(s, BZ3_STAGE_RLE);
+    if (!lease.ok()) return cudaErrorMemoryAllocation;
     Arena& A = s->arena;
     A.reset();
     MrleDecScratch S;
@@ -234,6 +384,8 @@ cudaError_t run_lzp_decode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32 m
 }
 
 cudaError_t run_bwt(bz3_state* s, u8* d_in, u32 n, u8* d_out, s32* idx) {
+    ArenaLease lease(s, BZ3_STAGE_BWT);
+    if (!lease.ok()) return cudaErrorMemoryAllocation;
     SufsortBuffers B;
     if (!carve_sufsort(s, n, B)) return cudaErrorMemoryAllocation;
     BZ_CUDA_TRY(cudaMemsetAsync(d_in + n, 0, 16, s->stream));  // zero padding read by the 7-byte key kernel
@@ -254,6 +406,8 @@ cudaError_t run_bwt(bz3_state* s, u8* d_in, u32 n, u8* d_out, s32* idx) {
 }
 
 cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, int* status) {
+    ArenaLease lease(s, BZ3_STAGE_BWT);
+    if (!lease.ok()) return cudaErrorMemoryAllocation;
     Arena& A = s->arena;
     A.reset();
     UnbwtBuffers B;
@@ -293,15 +447,6 @@ struct KernelChoice {
 };
 KernelChoice g_choice;
 std::once_flag g_choice_once;
-
-int env_int(const char* name, int fallback) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : fallback;
-}
-bool env_set(const char* name) {
-    const char* v = getenv(name);
-    return v && *v;
-}
 
 cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* out_size) {
     s32* d_res = reinterpret_cast<s32*>(s->d_scal + 12);
@@ -791,7 +936,7 @@ void apply_default_kernels(bz3_state* s) {
 BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return nullptr;  // :536
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
         fprintf(stderr, "[bz3_b200] no CUDA device: this library has no CPU path\n");
         return nullptr;
     }
@@ -816,11 +961,11 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     ok = ok && cudaMalloc(&s->d_lut, sizeof(s32) * kLzpSlots) == cudaSuccess;
     ok = ok && cudaMalloc(&s->d_scal, 256 * sizeof(u32)) == cudaSuccess;
     ok = ok && cudaMallocHost(&s->h_scal, 1024 * sizeof(u32)) == cudaSuccess;
-    if (ok) {
+    total += sizeof(s32) * kLzpSlots;
+    if (ok) {   // the stage workspace is shared by the states of the device (ArenaPool above)
         size_t a = sufsort_arena_bytes(n), b = other_arena_bytes(n);
-        s->arena.size = a > b ? a : b;
-        ok = cudaMalloc(&s->arena.base, s->arena.size) == cudaSuccess;
-        total += s->arena.size + sizeof(s32) * kLzpSlots;
+        s->arena_need = a > b ? a : b;
+        ok = s->pool_attached = pool_attach(dev, s->arena_need);
     }
     for (int i = 0; i < BZ3_STAGE_COUNT && ok; i++)
         ok = cudaEventCreate(&s->clk.a[i]) == cudaSuccess && cudaEventCreate(&s->clk.b[i]) == cudaSuccess;
@@ -846,7 +991,7 @@ BZIP3_API void bz3_free(struct bz3_state* s) {
     if (s->d_lut) cudaFree(s->d_lut);
     if (s->d_scal) cudaFree(s->d_scal);
     if (s->h_scal) cudaFreeHost(s->h_scal);
-    if (s->arena.base) cudaFree(s->arena.base);
+    if (s->pool_attached) pool_detach(s->device);
     for (int i = 0; i < BZ3_STAGE_COUNT; i++) {
         if (s->clk.a[i]) cudaEventDestroy(s->clk.a[i]);
         if (s->clk.b[i]) cudaEventDestroy(s->clk.b[i]);
@@ -1144,6 +1289,13 @@ BZIP3_API int bz3_b200_device_count(void) {
 }
 BZIP3_API int bz3_b200_state_device(struct bz3_state* s) { return s->device; }
 BZIP3_API size_t bz3_b200_device_bytes(struct bz3_state* s) { return s->device_bytes; }
+BZIP3_API size_t bz3_b200_workspace_bytes(struct bz3_state* s) {   // the device's shared stage workspaces, all slots
+    ArenaPool& P = g_pool[s->device];
+    std::lock_guard<std::mutex> lk(P.m);
+    size_t total = 0;
+    for (int k = 0; k < P.nslots; k++) total += P.slot[k].size;
+    return total;
+}
 BZIP3_API void bz3_b200_stats_reset(struct bz3_state* s) {
     memset(s->stage_ms, 0, sizeof s->stage_ms);
     s->launches = 0;

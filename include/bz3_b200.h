@@ -25,7 +25,12 @@ enum {
 /* number of CUDA devices visible / device a state lives on */
 BZIP3_API int bz3_b200_device_count(void);
 BZIP3_API int bz3_b200_state_device(struct bz3_state *state);
+/* device memory a state owns (three block buffers + LZP table) ... */
 BZIP3_API size_t bz3_b200_device_bytes(struct bz3_state *state);
+/* ... and the stage workspaces (mRLE / suffix sort / inverse BWT scratch, 48 B per byte of block) that all states of
+ * the state's device share: BZ3_B200_ARENAS of them (default 2), leased per stage call, sized for the largest live
+ * state, released with the last state.  Replaces the per-state `sais_array` of src/libbz3.c:498-504, 549-551. */
+BZIP3_API size_t bz3_b200_workspace_bytes(struct bz3_state *state);
 
 /* Device-resident codec: stage `size` bytes into the state, run the block codec without host copies,
  * fetch the result.  encode_resident/decode_resident return what bz3_encode_block/bz3_decode_block

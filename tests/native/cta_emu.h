@@ -31,6 +31,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -489,6 +490,8 @@ inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cuda
 constexpr unsigned cudaStreamNonBlocking = 1;
 template <class T>
 inline cudaError_t cudaMalloc(T** p, size_t n) {
+    if (const char* cap = getenv("BZ_EMU_MALLOC_MAX"))   // test hook: a "device" that cannot serve larger requests
+        if (n > strtoull(cap, nullptr, 10)) { *p = nullptr; return cudaErrorMemoryAllocation; }
     *p = static_cast<T*>(aligned_alloc(256, (n + 255) & ~(size_t)255));
     if (*p) memset(*p, 0xCD, n);   // device memory is not zeroed
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;

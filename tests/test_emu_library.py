@@ -197,3 +197,100 @@ def test_default_kernels_come_from_the_self_test(emulib):
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
     assert "CHOICE 6 8 2" in out.stdout or "CHOICE 6 9 2" in out.stdout, out.stdout + out.stderr
     assert "EXACT True" in out.stdout, out.stdout + out.stderr
+
+
+def test_stage_workspaces_are_shared_by_the_states_of_a_device(emulib, st):
+    """The 48 B/B scratch of mRLE / suffix sort / inverse BWT is a per-device pool leased per stage call (ArenaPool in
+    bz3_api.cu), not a per-state allocation: what a state owns is three block buffers and the LZP table."""
+    L = emulib
+    base = L.bz3_b200_workspace_bytes(st.handle)
+    own = L.bz3_b200_device_bytes(st.handle)
+    assert 0 < own < 3.2 * bzip3_b200.bound(BS) + (1 << 20) + 4096
+    assert 2 * 48 * BS > base >= 48 * BS   # a lone state: one workspace, sized for its block size
+    with bzip3_b200.Bz3State(BS) as s2:    # from the second state on there are two (BZ3_B200_ARENAS), and never more
+        two = L.bz3_b200_workspace_bytes(s2.handle)
+        assert two == 2 * base
+        with bzip3_b200.Bz3State(BS) as s2b:
+            assert L.bz3_b200_workspace_bytes(s2b.handle) == two
+        with bzip3_b200.Bz3State(4 * BS) as s3:   # a larger one grows the shared workspaces
+            grown = L.bz3_b200_workspace_bytes(s3.handle)
+            assert grown >= 2 * 48 * 4 * BS and L.bz3_b200_workspace_bytes(st.handle) == grown
+            data = synth.zipf_text(1300, seed=11).tobytes()
+            want = refs.oracle_encode_block(data, 4 * BS)
+            enc, r = s3.encode_block(data)
+            assert r == want[1] and enc == want[0]
+        data = synth.log_stream(1300, seed=12).tobytes()   # the smaller states keep working in the grown workspaces
+        want = refs.oracle_encode_block(data, BS)
+        enc, r = s2.encode_block(data)
+        assert r == want[1] and enc == want[0]
+        dec, r = st.decode_block(enc, len(data))
+        assert r == len(data) and dec == data
+
+
+def test_one_workspace_serves_a_batch_of_blocks(emulib):
+    """BZ3_B200_ARENAS=1: the host threads of bz3_encode_blocks / bz3_decode_blocks queue for the only workspace."""
+    import subprocess
+    import sys
+    script = (
+        "import sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "import bzip3_b200\n"
+        "from bzip3_b200 import synth\n"
+        "from tests import refs\n"
+        "bs = %d\n"
+        "datas = [synth.zipf_text(900 + 100 * k, seed=k).tobytes() for k in range(5)]\n"
+        "states = [bzip3_b200.Bz3State(bs) for _ in datas]\n"
+        "L = states[0].L\n"
+        "print('WORKSPACE', L.bz3_b200_workspace_bytes(states[0].handle) // (48 * bs))\n"
+        "bufs = []\n"
+        "for d in datas:\n"
+        "    b = np.zeros(bzip3_b200.bound(bs) + 64, np.uint8)\n"
+        "    b[:len(d)] = np.frombuffer(d, np.uint8)\n"
+        "    bufs.append(b)\n"
+        "sizes = [len(d) for d in datas]\n"
+        "out = bzip3_b200.encode_blocks(states, bufs, sizes)\n"
+        "ok = all(bytes(b[:r]) == refs.oracle_encode_block(d, bs)[0] for d, b, r in zip(datas, bufs, out))\n"
+        "errs = bzip3_b200.decode_blocks(states, bufs, [len(b) for b in bufs], out, sizes)\n"
+        "ok = ok and all(e == 0 and bytes(b[:len(d)]) == d for d, b, e in zip(datas, bufs, errs))\n"
+        "for s in states: s.close()\n"
+        "with bzip3_b200.Bz3State(bs) as s:\n"
+        "    ok = ok and s.encode_block(datas[0])[0] == refs.oracle_encode_block(datas[0], bs)[0]\n"
+        "print('EXACT', ok)\n" % (ROOT, BS))
+    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_ARENAS="1", BZ3_B200_AUTOSELECT="0")
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
+    assert "WORKSPACE 1" in out.stdout, out.stdout + out.stderr
+    assert "EXACT True" in out.stdout, out.stdout + out.stderr
+
+
+def test_out_of_device_memory_is_reported_by_bz3_new_and_spares_the_live_states(emulib):
+    """A state whose workspace does not fit makes bz3_new return NULL (as the reference's does on a failed malloc,
+    src/libbz3.c:553-561); the states that already exist keep their workspaces and keep coding."""
+    import subprocess
+    import sys
+    script = (
+        "import sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import bzip3_b200\n"
+        "from bzip3_b200 import synth\n"
+        "from tests import refs\n"
+        "bs = %d\n"
+        "L = bzip3_b200.lib()\n"
+        "a = bzip3_b200.Bz3State(bs)\n"
+        "b = bzip3_b200.Bz3State(bs)\n"
+        "before = L.bz3_b200_workspace_bytes(a.handle)\n"
+        "print('BIG', L.bz3_new(8 * bs))\n"
+        "print('SAME', L.bz3_b200_workspace_bytes(a.handle) == before)\n"
+        "data = synth.zipf_text(1000, seed=4).tobytes()\n"
+        "want = refs.oracle_encode_block(data, bs)\n"
+        "ok = True\n"
+        "for s in (a, b):\n"
+        "    enc, r = s.encode_block(data)\n"
+        "    dec, r2 = s.decode_block(enc, len(data))\n"
+        "    ok = ok and r == want[1] and enc == want[0] and dec == data\n"
+        "print('EXACT', ok)\n" % (ROOT, BS))
+    cap = 48 * 3 * BS   # enough for the workspace of a BS state (and for block buffers), not for an 8 * BS state
+    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="0", BZ_EMU_MALLOC_MAX=str(cap))
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
+    assert "BIG None" in out.stdout, out.stdout + out.stderr
+    assert "SAME True" in out.stdout and "EXACT True" in out.stdout, out.stdout + out.stderr
