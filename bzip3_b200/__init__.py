@@ -133,7 +133,7 @@ def _ptr(a: np.ndarray):
 
 
 class Bz3State:
-    """Owns one `struct bz3_state` (device arena + stream).  Mirrors bz3_new / bz3_free."""
+    """Owns one `struct bz3_state` (device block buffers + stream; stage workspaces are shared per device).  Mirrors bz3_new / bz3_free."""
 
     def __init__(self, block_size: int):
         self.L = lib()
