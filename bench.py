@@ -429,7 +429,7 @@ def run_b200_arm(args, rank, world, local_rank):
                        "bytes_per_gpu": total, "parallelism": f"blocks sharded {world} way(s), one stream per block",
                        "l2": "256 MiB flush buffer written before every timed step; block buffers + shared stage workspaces >> 126 MB L2",
                        "kernels_in_effect": {"entropy_encoder": int(cm_variants[0]), "entropy_decoder": int(cm_variants[1]),
-                                             "lzp": int(lzp_variant),
+                                             "lzp": int(lzp_variant), "retired_after_checksum_failure": int(L.bz3_b200_demotions()),
                                              "how": "on-device self-test at the first bz3_new (DESIGN.md 6c); 0/0/3 = round-1 kernels"},
                        "hbm_bytes": {"per_block_state": int(L.bz3_b200_device_bytes(states[0].handle)),
                                      "shared_stage_workspaces": int(L.bz3_b200_workspace_bytes(states[0].handle))},

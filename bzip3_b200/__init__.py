@@ -83,6 +83,8 @@ def lib():
     L.bz3_b200_state_device.argtypes = [C.c_void_p]
     L.bz3_b200_device_bytes.restype = C.c_size_t
     L.bz3_b200_device_bytes.argtypes = [C.c_void_p]
+    L.bz3_b200_demotions.restype = C.c_int
+    L.bz3_b200_demotions.argtypes = []
     L.bz3_b200_workspace_bytes.restype = C.c_size_t
     L.bz3_b200_workspace_bytes.argtypes = [C.c_void_p]
     L.bz3_b200_upload.restype = C.c_int

@@ -5,6 +5,7 @@
 // bz3_encode_block / bz3_decode_block (reference src/libbz3.c:585-809); the batch entry points restate
 // bz3_encode_blocks / bz3_decode_blocks (:813-872) with one host thread + one CUDA stream per block.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #if !defined(BZ_EMU) || defined(BZ_EMU_SPAWN_TEST)
@@ -101,6 +102,7 @@ struct bz3_state {
     int variant[BZ3_STAGE_COUNT];
     int cm_enc, cm_dec;   // entropy-stage kernel selection in effect (see kernel_autoselect)
     int lzp_default;      // LZP kernels used when variant[BZ3_STAGE_LZP] == 0
+    bool dec_promoted, lzp_promoted;   // cm_dec / lzp_default were put there by the self-test (see decode_checked)
     cudaEvent_t sort_ev[2 * 40];
 };
 
@@ -444,9 +446,12 @@ cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, i
 // kernels' bytes on the test inputs AND are faster there.
 struct KernelChoice {
     int cm_enc = 0, cm_dec = 0, lzp = 3;   // proven kernels: chunked encoder 0, tree decoder 0, one-window LZP (3)
+    bool dec_promoted = false, lzp_promoted = false;   // decoder / LZP kernels chosen by the self-test, not by the user
 };
 KernelChoice g_choice;
 std::once_flag g_choice_once;
+std::mutex g_choice_mutex;          // g_choice after the once-only self-test (demotion, see decode_checked)
+std::atomic<int> g_demotions{0};    // times a promoted decode-side kernel was caught by the block checksum
 
 cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* out_size) {
     s32* d_res = reinterpret_cast<s32*>(s->d_scal + 12);
@@ -487,6 +492,11 @@ cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s
         BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<2, 1>)(d_in, insize, d_out, n);
     else
         BZ_LAUNCH(1, kCmDecThreads, kCmDecSmemBytes, s->stream, cm_decode_tree_kernel)(d_in, insize, d_out, n);
+#if defined(BZ_EMU)
+    // test hook of the emulator build (tests/test_emu_library.py): a promoted decoder that gets one byte wrong
+    if (const char* sab = getenv("BZ_EMU_SABOTAGE_DEC_N"))
+        if (s->cm_dec >= 4 && n == atoi(sab) && n > 0) d_out[n / 2] ^= 0x20;
+#endif
     BZ_NOTE_LAUNCH();
     return cudaGetLastError();
 }
@@ -638,6 +648,50 @@ int decode_core(bz3_state* s, int pay_buf, size_t pay_off, const DecodeHeader& H
     *out_buf = cur;
     *out_size = cur_size;
     return BZ3_OK;
+}
+
+// decode_core with a second opinion.  The newer decode-side kernels (entropy decoders 8 / 9, bulk LZP decoder) become
+// defaults on the strength of the start-up self-test alone.  Every block carries a checksum, so a block that fails
+// under such a promoted kernel -- wrong checksum or any other error -- is decoded once more with the round-1 kernels
+// (the payload buffer is never written by the stages, so it is still there).  Their verdict is what the caller gets,
+// which keeps the error behaviour the reference's on hostile input; and if THEY decode the block, the promoted
+// kernel was wrong: it is retired for the whole process, counted (bz3_b200_demotions) and reported on stderr.
+// Kernels the user selected (bz3_b200_set_variant, BZ3_B200_CM_DEC / BZ3_B200_LZP) get no second opinion: they are
+// what is being tested.
+void retire_promoted_kernels(bz3_state* s) {
+    s->cm_dec = s->dec_promoted ? 0 : s->cm_dec;
+    s->lzp_default = s->lzp_promoted ? 3 : s->lzp_default;
+    s->dec_promoted = s->lzp_promoted = false;
+}
+
+int decode_checked(bz3_state* s, int pay_buf, size_t pay_off, const DecodeHeader& H, size_t buffer_size, s32 orig_size,
+                   int* out_buf, s32* out_size, bool* crc_ok) {
+    if ((s->dec_promoted || s->lzp_promoted) && g_demotions.load() > 0) retire_promoted_kernels(s);
+    const bool dec_cand = s->dec_promoted && s->cm_dec != 0;
+    const bool lzp_cand = s->lzp_promoted && s->variant[BZ3_STAGE_LZP] == 0 && s->lzp_default != 3 && (H.model & 2);
+    int e = decode_core(s, pay_buf, pay_off, H, buffer_size, orig_size, out_buf, out_size, crc_ok);
+    if ((e == BZ3_OK && *crc_ok) || !(dec_cand || lzp_cand)) return e;
+    const int dec0 = s->cm_dec, lzp0 = s->lzp_default;
+    s->cm_dec = dec_cand ? 0 : dec0;
+    s->lzp_default = lzp_cand ? 3 : lzp0;
+    *crc_ok = false;
+    e = decode_core(s, pay_buf, pay_off, H, buffer_size, orig_size, out_buf, out_size, crc_ok);
+    if (e == BZ3_OK && *crc_ok) {   // the block was fine, the promoted kernel was not
+        if (g_demotions.fetch_add(1) == 0)
+            fprintf(stderr, "[bz3_b200] WARNING: a block that failed with entropy decoder %d / LZP %d decodes with the round-1 "
+                            "kernels; the newer kernels are retired for this process (please report)\n", dec0, lzp0);
+        {
+            std::lock_guard<std::mutex> lk(g_choice_mutex);
+            g_choice.cm_dec = g_choice.dec_promoted ? 0 : g_choice.cm_dec;
+            g_choice.lzp = g_choice.lzp_promoted ? 3 : g_choice.lzp;
+            g_choice.dec_promoted = g_choice.lzp_promoted = false;
+        }
+        retire_promoted_kernels(s);
+    } else {                        // the input is bad: both kernels say so, the promoted ones stay
+        s->cm_dec = dec0;
+        s->lzp_default = lzp0;
+    }
+    return e;
 }
 
 bool use_device(bz3_state* s) { return cudaSetDevice(s->device) == cudaSuccess; }
@@ -920,15 +974,20 @@ void kernel_autoselect(bz3_state* s) {
 #endif
         }
     }
+    c.dec_promoted = !pin.dec && c.cm_dec != 0;
+    c.lzp_promoted = !pin.lzp && c.lzp != 3;
     g_choice = c;
     if (getenv("BZ3_B200_VERBOSE"))
         fprintf(stderr, "[bz3_b200] kernels in effect: entropy encoder %d, decoder %d, LZP %d -- %s\n", c.cm_enc, c.cm_dec, c.lzp, how);
 }
 
 void apply_default_kernels(bz3_state* s) {
+    std::lock_guard<std::mutex> lk(g_choice_mutex);
     s->cm_enc = g_choice.cm_enc;
     s->cm_dec = g_choice.cm_dec;
     s->lzp_default = g_choice.lzp;
+    s->dec_promoted = g_choice.dec_promoted;
+    s->lzp_promoted = g_choice.lzp_promoted;
 }
 
 }  // namespace
@@ -1097,7 +1156,7 @@ BZIP3_API int32_t bz3_b200_decode_resident(struct bz3_state* s, int32_t compress
     int ob = in_buf;
     s32 osz = 0;
     bool crc_ok = false;
-    int e = decode_core(s, in_buf, (size_t)H.hdr, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
+    int e = decode_checked(s, in_buf, (size_t)H.hdr, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
     clocks_collect(s, 1);
     if (e != BZ3_OK) { s->last_error = (s8)e; return -1; }
     s->resident_buf = ob;
@@ -1151,7 +1210,7 @@ BZIP3_API int32_t bz3_decode_block(struct bz3_state* s, uint8_t* buffer, size_t 
     int ob = 0;
     s32 osz = 0;
     bool crc_ok = false;
-    int e = decode_core(s, 0, 0, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
+    int e = decode_checked(s, 0, 0, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
     if (e != BZ3_OK) { s->last_error = (s8)e; clocks_collect(s, 1); return -1; }
     s->last_error = BZ3_OK;
     {
@@ -1341,14 +1400,24 @@ BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant)
     // the entropy stage has separate encoder / decoder selections: BZ3_STAGE_CM sets both (0 = defaults),
     // BZ3_STAGE_CM + 100 the encoder alone, BZ3_STAGE_CM + 200 the decoder alone
     if (stage == BZ3_STAGE_CM) {
-        s->cm_enc = variant ? variant : g_choice.cm_enc;
-        s->cm_dec = variant ? variant : g_choice.cm_dec;
+        const int lzp_keep = s->lzp_default;
+        const bool lzp_flag = s->lzp_promoted;
+        apply_default_kernels(s);
+        s->lzp_default = lzp_keep;
+        s->lzp_promoted = lzp_flag;
+        if (variant) {
+            s->cm_enc = s->cm_dec = variant;
+            s->dec_promoted = false;   // the user's choice: no second opinion (decode_checked)
+        }
     } else if (stage == BZ3_STAGE_CM + 100) {
         s->cm_enc = variant;
     } else if (stage == BZ3_STAGE_CM + 200) {
         s->cm_dec = variant;
+        s->dec_promoted = false;
     }
 }
+
+BZIP3_API int bz3_b200_demotions(void) { return g_demotions.load(); }
 
 // ------------------------------------------------------------------ single stages on host buffers (tests)
 namespace {

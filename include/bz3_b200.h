@@ -70,6 +70,11 @@ BZIP3_API int bz3_b200_stage_cm_decode(struct bz3_state *state, const uint8_t *i
  * BZ3_STAGE_CM + 100 the encoder, BZ3_STAGE_CM + 200 the decoder.  get_variant reports the selection in effect. */
 BZIP3_API void bz3_b200_set_variant(struct bz3_state *state, int stage, int variant);
 BZIP3_API int bz3_b200_get_variant(struct bz3_state *state, int stage);
+/* Decode-side kernels that the start-up self-test made the defaults (entropy decoders 8 / 9, the bulk LZP decoder) are
+ * backed by the block checksum: a block that fails under them is decoded again with the round-1 kernels, whose verdict
+ * the caller gets (so hostile input still yields the reference's error codes, src/libbz3.c:739-809); if the round-1
+ * kernels decode it, the newer kernels are retired for the process.  Number of times that happened (0 = never). */
+BZIP3_API int bz3_b200_demotions(void);
 /* the self-test behind the defaults, run in the calling process on `device` (used by the helper bz3_selftest, which the
  * library spawns so that a misbehaving candidate kernel can never take the caller's CUDA context down); returns 0 and
  * the kernels it would choose */

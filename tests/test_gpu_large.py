@@ -65,3 +65,9 @@ def test_batch_of_16mib_blocks_matches_reference():
 @pytest.mark.skipif(os.environ.get("BZ3_TEST_HUGE") != "1", reason="set BZ3_TEST_HUGE=1 (several minutes of GPU time)")
 def test_roundtrip_256mib_block():
     roundtrip(256, synth.source_corpus, check_reference=False)
+
+
+def test_no_promoted_kernel_was_retired():
+    """Runs last in this module: the round trips above used the kernels the self-test chose; none of them may have needed
+    the round-1 kernels' second opinion on a good block (decode_checked in bz3_api.cu)."""
+    assert bzip3_b200.lib().bz3_b200_demotions() == 0

@@ -351,3 +351,5 @@ def test_default_kernels_in_effect(st, capsys):
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BZ3_B200_AUTOSELECT="0"), cwd=refs.ROOT,
                          capture_output=True, text=True, timeout=300)
     assert "CHOICE 0 0 3" in out.stdout, out.stdout + out.stderr
+    # no promoted kernel was caught out by a block checksum while the tests above ran (decode_checked in bz3_api.cu)
+    assert L.bz3_b200_demotions() == 0
