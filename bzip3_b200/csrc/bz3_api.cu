@@ -361,6 +361,7 @@ cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* 
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
+    BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));   // see run_cm_encode: nothing waits in a queue behind a long kernel
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
     BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
     *result = (s32)s->h_scal[8];
@@ -379,6 +380,7 @@ cudaError_t run_lzp_decode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32 m
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_decode_warp_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
+    BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));   // see run_cm_encode: nothing waits in a queue behind a long kernel
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
     BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
     *result = (s32)s->h_scal[8];
@@ -467,6 +469,10 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
         BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<0>)(d_in, n, d_out, d_res);
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
+    // Nothing is queued behind a long single-CTA kernel: with more streams than hardware queues (32 at most,
+    // CUDA_DEVICE_MAX_CONNECTIONS) a copy or launch waiting in a queue for THIS block's coder would hold up the
+    // launches of every other block that shares the queue -- and blocks in flight are the throughput of this library.
+    BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
     BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 12, d_res, 4, cudaMemcpyDeviceToHost, s->stream));
     BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
     *out_size = (s32)s->h_scal[12];
@@ -498,7 +504,8 @@ cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s
         if (s->cm_dec >= 4 && n == atoi(sab) && n > 0) d_out[n / 2] ^= 0x20;
 #endif
     BZ_NOTE_LAUNCH();
-    return cudaGetLastError();
+    BZ_CUDA_TRY(cudaGetLastError());
+    return cudaStreamSynchronize(s->stream);   // see run_cm_encode: the inverse BWT's launches must not queue behind the decoder
 }
 
 // ---------------------------------------------------------------------------------- block encode

@@ -19,7 +19,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KSO, SSO = "/tmp/libemucheck_tsan.so", "/tmp/libemustages_tsan.so"
+KSO, SSO, LSO = "/tmp/libemucheck_tsan.so", "/tmp/libemustages_tsan.so", "/tmp/libbzip3_emu_tsan.so"
 N = 1500
 
 
@@ -36,7 +36,24 @@ def child(kind, variant):
         O.orc_bwt(refs.ptr(d), refs.ptr(o), len(d))
         return o[:len(d)].copy()
 
-    if kind in ("enc", "dec"):
+    if kind == "lib":   # the whole library: host threads of the batch API queueing for `variant` stage workspaces
+        import bzip3_b200
+        bs = 66 * 1024
+        datas = [synth.zipf_text(700 + 60 * k, seed=k).tobytes() for k in range(4)]
+        states = [bzip3_b200.Bz3State(bs) for _ in datas]
+        bufs = []
+        for d in datas:
+            b = np.zeros(bzip3_b200.bound(bs) + 64, np.uint8)
+            b[:len(d)] = np.frombuffer(d, np.uint8)
+            bufs.append(b)
+        sizes = [len(d) for d in datas]
+        out = bzip3_b200.encode_blocks(states, bufs, sizes)
+        ok = all(bytes(b[:r]) == refs.oracle_encode_block(d, bs)[0] for d, b, r in zip(datas, bufs, out))
+        errs = bzip3_b200.decode_blocks(states, bufs, [len(b) for b in bufs], out, sizes)
+        ok = ok and all(e == 0 and bytes(b[:len(d)]) == d for d, b, e in zip(datas, bufs, errs))
+        for s in states:
+            s.close()
+    elif kind in ("enc", "dec"):
         L = C.CDLL(KSO)
         L.emu_cm_encode.restype = C.c_int32
         L.emu_cm_encode.argtypes = [C.c_int, u8p, C.c_int32, u8p]
@@ -104,11 +121,18 @@ def main():
     flags = ["g++", "-O1", "-g", "-fsanitize=thread", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-x", "c++"]
     subprocess.check_call(flags + ["-o", KSO, os.path.join(native, "emu_check.cpp"), os.path.join(native, "cta_emu.cpp")])
     subprocess.check_call(flags + ["-o", SSO, os.path.join(native, "emu_stages.cpp"), os.path.join(native, "cta_emu.cpp")])
+    subprocess.check_call(flags[:-2] + ["-DBZ_EMU", "-include", os.path.join(native, "cta_emu.h"), "-x", "c++", "-o", LSO,
+                                        os.path.join(ROOT, "bzip3_b200", "csrc", "bz3_api.cu"), os.path.join(native, "cta_emu.cpp"),
+                                        "-lpthread"])
     tsan = subprocess.check_output(["g++", "-print-file-name=libtsan.so"], text=True).strip()
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
-    jobs = [("enc", v) for v in (0, 2, 4, 6)] + [("dec", v) for v in (0, 3, 4, 5, 6, 7, 8, 9)] + [("lzp", 0), ("lzp", 2), ("stages", 0)]
+    jobs = [("enc", v) for v in (0, 2, 4, 6)] + [("dec", v) for v in (0, 3, 4, 5, 6, 7, 8, 9)] + [("lzp", 0), ("lzp", 2), ("stages", 0), ("lib", 1), ("lib", 2)]
+    only = os.environ.get("EMU_TSAN_ONLY")   # e.g. EMU_TSAN_ONLY=lib,stages
+    jobs = [j for j in jobs if not only or j[0] in only.split(",")]
     bad = 0
     for kind, v in jobs:
+        if kind == "lib":
+            env = dict(env, BZ3_B200_LIB=LSO, BZ3_B200_ARENAS=str(v), BZ3_B200_AUTOSELECT="0")
         out = subprocess.run([sys.executable, os.path.abspath(__file__), kind, str(v)], env=env, capture_output=True, text=True)
         text = out.stdout + out.stderr
         result = "bit-exact" if "RESULT bit-exact" in text else "NO RESULT / WRONG OUTPUT"
@@ -117,7 +141,8 @@ def main():
             fr = re.findall(r"#0 (?:void )?([\w:<>, ]+?)\(", blk)
             key = " <-> ".join(sorted(set(f.strip() for f in fr[:2])))
             races[key] = races.get(key, 0) + 1
-        name = {"enc": "CM encoder", "dec": "CM decoder", "lzp": "LZP encoder+decoder variant", "stages": "CRC / mRLE / BWT / inverse BWT"}[kind]
+        name = {"enc": "CM encoder", "dec": "CM decoder", "lzp": "LZP encoder+decoder variant", "stages": "CRC / mRLE / BWT / inverse BWT",
+                "lib": "library, 4-block batch, workspaces"}[kind]
         line = "%-30s %d: %s, " % (name, v, result)
         line += "no race reported" if not races else "; ".join("%d x %s" % (c, k) for k, c in races.items())
         print(line, flush=True)
