@@ -83,6 +83,11 @@ def lib():
     L.bz3_b200_state_device.argtypes = [C.c_void_p]
     L.bz3_b200_device_bytes.restype = C.c_size_t
     L.bz3_b200_device_bytes.argtypes = [C.c_void_p]
+    u64p = C.POINTER(C.c_uint64)
+    L.bz3_b200_encode_fd.restype = C.c_int
+    L.bz3_b200_encode_fd.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_int, u64p, u64p]
+    L.bz3_b200_decode_fd.restype = C.c_int
+    L.bz3_b200_decode_fd.argtypes = [C.c_int, C.c_int, C.c_int, u64p, u64p]
     L.bz3_b200_demotions.restype = C.c_int
     L.bz3_b200_demotions.argtypes = []
     L.bz3_b200_workspace_bytes.restype = C.c_size_t

@@ -37,6 +37,7 @@ extern char** environ;
 #include "sufsort.cuh"
 #include "unbwt.cuh"
 #include "cm.cuh"
+#include "stream.h"
 
 using namespace bz3;
 
@@ -1425,6 +1426,68 @@ BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant)
 }
 
 BZIP3_API int bz3_b200_demotions(void) { return g_demotions.load(); }
+
+// ------------------------------------------------------------------ the CLI's container with a deep block queue (stream.h)
+namespace {
+void* stream_host_alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, n) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void stream_host_free(void* p) { cudaFreeHost(p); }
+void stream_thread_init(int dev) { cudaSetDevice(dev); }   // the workers' states live on the caller's current device
+int stream_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : 0;
+}
+
+int stream_depth(int32_t block_size, int in_flight) {
+    if (in_flight > 256) in_flight = 256;
+    if (in_flight > 0) return in_flight;
+    int depth = 64;   // blocks beyond the SM count only wait; 64 is also where the reference's -j stops (src/main.c:213)
+#if !defined(BZ_EMU)
+    int dev = 0, sms = 0;
+    size_t free_b = 0, total_b = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        depth = std::min(depth, sms);
+    const size_t n = block_bound((size_t)block_size) + 64;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const size_t ws = 2 * std::max(sufsort_arena_bytes(n), other_arena_bytes(n)) + (size_t(1) << 30);
+        const size_t per_state = 3 * align_up(n + 256) + (size_t(2) << 20);
+        depth = free_b > ws + per_state ? (int)std::min<size_t>((size_t)depth, (free_b - ws) / per_state) : 1;
+    }
+    depth = (int)std::min<size_t>((size_t)depth, std::max<size_t>(1, (size_t(16) << 30) / n));   // pinned host memory: 16 GiB at most
+#else
+    (void)block_size;
+    depth = 4;
+#endif
+    return depth < 1 ? 1 : depth;
+}
+}  // namespace
+
+BZIP3_API int bz3_b200_encode_fd(int in_fd, int out_fd, int32_t block_size, int in_flight, uint64_t* bytes_in, uint64_t* bytes_out) {
+    if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return BZ3_B200_ERR_BLOCK_SIZE;
+    u8 head[9] = {'B', 'Z', '3', 'v', '1'};
+    put32(head + 5, (u32)block_size);
+    if (out_fd >= 0 && !bz3stream::write_full(out_fd, head, 9)) return BZ3_B200_ERR_IO;
+    uint64_t out = 0;
+    int r = bz3stream::run(in_fd, out_fd, block_size, stream_depth(block_size, in_flight), false, bytes_in, &out, stream_host_alloc,
+                           stream_host_free, stream_thread_init, stream_device());
+    if (bytes_out) *bytes_out = out + 9;
+    return r;
+}
+
+BZIP3_API int bz3_b200_decode_fd(int in_fd, int out_fd, int in_flight, uint64_t* bytes_in, uint64_t* bytes_out) {
+    u8 head[9];
+    if (bz3stream::read_full(in_fd, head, 9) != 9 || memcmp(head, "BZ3v1", 5) != 0) return BZ3_B200_ERR_SIGNATURE;
+    const s32 block_size = (s32)get32(head + 5);
+    if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return BZ3_B200_ERR_BLOCK_SIZE;
+    uint64_t in = 0;
+    int r = bz3stream::run(in_fd, out_fd, block_size, stream_depth(block_size, in_flight), true, &in, bytes_out, stream_host_alloc,
+                           stream_host_free, stream_thread_init, stream_device());
+    if (bytes_in) *bytes_in = in + 9;
+    return r;
+}
 
 // ------------------------------------------------------------------ single stages on host buffers (tests)
 namespace {

@@ -75,6 +75,21 @@ BZIP3_API int bz3_b200_get_variant(struct bz3_state *state, int stage);
  * the caller gets (so hostile input still yields the reference's error codes, src/libbz3.c:739-809); if the round-1
  * kernels decode it, the newer kernels are retired for the process.  Number of times that happened (0 = never). */
 BZIP3_API int bz3_b200_demotions(void);
+
+/* The ".bz3" container of the reference's command line tool (src/main.c:157-482: "BZ3v1", s32 LE block size, then per
+ * block s32 LE coded size, s32 LE original size, coded bytes) over file descriptors, with a deep block queue instead of
+ * the reference's read-J / code-J / write-J batches (:352-478, J <= 64): a reader, `in_flight` workers (one state and
+ * stream each) and an in-order writer, each running as soon as its slot is ready.  in_flight <= 0 picks
+ * min(SM count, what device memory holds, 64).  The bytes written equal `bzip3 -e -b <block_size>`'s.
+ * decode_fd with out_fd < 0 only tests (`bzip3 -t`).  Return 0, a BZ3_ERR_* of the failing block (blocks before it have
+ * been written, as by the reference's loop), or one of the codes below. */
+#define BZ3_B200_ERR_IO (-20)         /* read / write failed */
+#define BZ3_B200_ERR_SIGNATURE (-21)  /* "Invalid signature." (src/main.c:186) */
+#define BZ3_B200_ERR_BLOCK_SIZE (-24) /* block size outside 65 KiB .. 511 MiB (:195) */
+#define BZ3_B200_ERR_HEADERS (-22)    /* "Inconsistent headers." (:265) */
+#define BZ3_B200_ERR_TRUNCATED (-23)  /* file ends inside a block (xread_noeof, :262-270) */
+BZIP3_API int bz3_b200_encode_fd(int in_fd, int out_fd, int32_t block_size, int in_flight, uint64_t *bytes_in, uint64_t *bytes_out);
+BZIP3_API int bz3_b200_decode_fd(int in_fd, int out_fd, int in_flight, uint64_t *bytes_in, uint64_t *bytes_out);
 /* the self-test behind the defaults, run in the calling process on `device` (used by the helper bz3_selftest, which the
  * library spawns so that a misbehaving candidate kernel can never take the caller's CUDA context down); returns 0 and
  * the kernels it would choose */

@@ -1,0 +1,94 @@
+"""The container front end with the deep block queue (bz3_b200_encode_fd / bz3_b200_decode_fd, csrc/stream.h) on the GPU:
+more blocks than queue slots, several blocks in flight, bytes compared with the reference tool's container built around
+the oracle's blocks (and with the reference binary where oracle/_ref travelled along)."""
+import ctypes as C
+import os
+import struct
+import subprocess
+
+import pytest
+
+import bzip3_b200
+from bzip3_b200 import synth
+from tests import refs
+
+pytestmark = pytest.mark.gpu
+BS = 1 << 20
+
+
+def container(data, bs):
+    out = bytearray(b"BZ3v1" + struct.pack("<i", bs))
+    for at in range(0, len(data), bs):
+        blk = data[at:at + bs]
+        enc, r, _ = refs.oracle_encode_block(blk, bs)
+        out += struct.pack("<ii", r, len(blk)) + enc[:r]
+    return bytes(out)
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    data = (synth.zipf_text(2_300_000, seed=21).tobytes() + bytes(300_000) + synth.log_stream(1_900_000, seed=22).tobytes()
+            + synth.source_corpus(1_200_000, seed=23).tobytes() + b"end")
+    return data, container(data, BS)
+
+
+def run_fd(fn, src_bytes, tmp_path, *args, test_only=False):
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.write_bytes(src_bytes)
+    fi = os.open(src, os.O_RDONLY)
+    fo = -1 if test_only else os.open(dst, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    nin, nout = C.c_uint64(0), C.c_uint64(0)
+    try:
+        rc = fn(fi, fo, *args, C.byref(nin), C.byref(nout))
+    finally:
+        os.close(fi)
+        if fo >= 0:
+            os.close(fo)
+    return rc, (b"" if test_only else dst.read_bytes()), nin.value, nout.value
+
+
+@pytest.mark.parametrize("depth", [1, 4, 0])
+def test_stream_roundtrip_bytes(tmp_path, corpus, depth):
+    L = bzip3_b200.lib()
+    data, want = corpus
+    rc, got, nin, nout = run_fd(L.bz3_b200_encode_fd, data, tmp_path, BS, depth)
+    assert rc == 0 and nin == len(data) and nout == len(want)
+    assert got == want
+    rc, back, nin, nout = run_fd(L.bz3_b200_decode_fd, want, tmp_path, depth)
+    assert rc == 0 and back == data
+    rc, _, _, nout = run_fd(L.bz3_b200_decode_fd, want, tmp_path, depth, test_only=True)
+    assert rc == 0 and nout == len(data)
+    assert L.bz3_b200_demotions() == 0
+
+
+def test_stream_damaged_block(tmp_path, corpus):
+    L = bzip3_b200.lib()
+    data, want = corpus
+    at = 9
+    c0 = struct.unpack_from("<i", want, at)[0]
+    second = at + 8 + c0
+    c1, o1 = struct.unpack_from("<ii", want, second)
+    bad = bytearray(want)
+    bad[second + 8 + c1 // 3] ^= 0x04
+    expect = refs.oracle_decode_block(bytes(bad[second + 8: second + 8 + c1]), o1, BS, err_init=55)
+    rc, back, _, _ = run_fd(L.bz3_b200_decode_fd, bytes(bad), tmp_path, 3)
+    assert expect[1] == -1 and rc == expect[2]
+    assert back == data[:BS]          # the block before the damaged one is out, nothing after it
+    rc, back, _, _ = run_fd(L.bz3_b200_decode_fd, want[:second + 8 + c1 // 2], tmp_path, 3)
+    assert rc == -23 and back == data[:BS]
+
+
+def test_command_line_tool(tmp_path, corpus):
+    cli = os.path.join(refs.ROOT, "bzip3_b200", "bz3b200")
+    if not os.path.exists(cli):
+        pytest.skip("bzip3_b200/bz3b200 not built")
+    data, want = corpus
+    r = subprocess.run([cli, "-e", "-b", "1", "-j", "5"], input=data, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want
+    if os.path.exists(refs.REF_CLI):
+        ref = subprocess.run([refs.REF_CLI, "-e", "-b", "1", "-j", "4"], input=data, capture_output=True, check=True, timeout=600).stdout
+        assert r.stdout == ref
+        assert subprocess.run([refs.REF_CLI, "-d"], input=r.stdout, capture_output=True, check=True, timeout=600).stdout == data
+    r = subprocess.run([cli, "-d", "-j", "3"], input=want, capture_output=True, timeout=600)
+    assert r.returncode == 0 and r.stdout == data
