@@ -989,6 +989,16 @@ void kernel_autoselect(bz3_state* s) {
         fprintf(stderr, "[bz3_b200] kernels in effect: entropy encoder %d, decoder %d, LZP %d -- %s\n", c.cm_enc, c.cm_dec, c.lzp, how);
 }
 
+// Per-device constants (CRC tables in constant memory, the kernels' shared-memory opt-in): once per device, not once per
+// state -- states are also created while other blocks are running (stream.h), and there is no reason to rewrite a
+// constant bank that running kernels read.
+bool device_setup(int dev) {
+    static std::once_flag once[kMaxDevices];
+    static bool good[kMaxDevices];
+    std::call_once(once[dev], [dev] { good[dev] = crc_upload_tables() == cudaSuccess && cm_set_smem_attrs() == cudaSuccess; });
+    return good[dev];
+}
+
 void apply_default_kernels(bz3_state* s) {
     std::lock_guard<std::mutex> lk(g_choice_mutex);
     s->cm_enc = g_choice.cm_enc;
@@ -1019,7 +1029,7 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     const size_t n = block_bound((size_t)block_size) + 64;
     s->cap = align_up(n + 256);
     bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && crc_upload_tables() == cudaSuccess && cm_set_smem_attrs() == cudaSuccess;
+    ok = ok && device_setup(dev);
     size_t total = 0;
     for (int i = 0; i < 3 && ok; i++) {
         ok = cudaMalloc(&s->d_buf[i], s->cap) == cudaSuccess;
