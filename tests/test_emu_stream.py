@@ -234,3 +234,9 @@ def test_command_line_tool(L, tmp_path):
     assert r.returncode == 1 and b"Failed to decode" in r.stderr
     r = subprocess.run([cli, "-d"], input=b"not a bz3 file", env=env, capture_output=True, timeout=300)
     assert r.returncode == 1 and b"invalid signature" in r.stderr
+
+
+def test_gpu_many_blocks_check_runs_on_the_emulator(L):
+    """The body of the GPU test of many blocks in flight (tests/test_gpu_stream.py), at emulator size."""
+    from tests.test_gpu_stream import many_blocks_check
+    many_blocks_check(L, BS, 6, 1300)

@@ -92,3 +92,37 @@ def test_command_line_tool(tmp_path, corpus):
         assert subprocess.run([refs.REF_CLI, "-d"], input=r.stdout, capture_output=True, check=True, timeout=600).stdout == data
     r = subprocess.run([cli, "-d", "-j", "3"], input=want, capture_output=True, timeout=600)
     assert r.returncode == 0 and r.stdout == data
+
+
+def many_blocks_check(L, bs, nblk, nbytes):
+    import numpy as np
+    gens = (synth.zipf_text, synth.log_stream, synth.source_corpus)
+    datas = [gens[k % 3](nbytes - (nbytes // 256) * (k % 5), seed=100 + k).tobytes() for k in range(nblk)]
+    states = [bzip3_b200.Bz3State(bs) for _ in datas]
+    try:
+        ws = L.bz3_b200_workspace_bytes(states[0].handle)
+        own = L.bz3_b200_device_bytes(states[0].handle)
+        assert 2 * 48 * bs <= ws < 2 * 56 * bs and own < 3.3 * bzip3_b200.bound(bs) + (2 << 20)
+        bufs = []
+        for d in datas:
+            b = np.zeros(bzip3_b200.bound(bs) + 64, np.uint8)
+            b[:len(d)] = np.frombuffer(d, np.uint8)
+            bufs.append(b)
+        sizes = bzip3_b200.encode_blocks(states, bufs, [len(d) for d in datas])
+        assert all(s.last_error == 0 for s in states)
+        for k in range(0, nblk, 5):
+            assert bytes(bufs[k][:sizes[k]]) == refs.oracle_encode_block(datas[k], bs)[0], k
+        bzip3_b200.decode_blocks(states, bufs, [len(b) for b in bufs], sizes, [len(d) for d in datas])
+        for d, b, s in zip(datas, bufs, states):
+            assert s.last_error == 0 and bytes(b[:len(d)]) == d
+        assert L.bz3_b200_workspace_bytes(states[0].handle) == ws
+        assert L.bz3_b200_demotions() == 0
+    finally:
+        for s in states:
+            s.close()
+
+
+def test_many_blocks_in_flight_share_two_workspaces():
+    """48 states / streams at once (more than the 32 hardware queues), all leasing the device's two stage workspaces:
+    bit-exact against the oracle, and the device footprint is 48 small states + 2 workspaces, not 48 workspaces."""
+    many_blocks_check(bzip3_b200.lib(), 256 << 10, 48, (256 << 10) - 8)
