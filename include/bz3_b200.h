@@ -73,7 +73,9 @@ BZIP3_API int bz3_b200_get_variant(struct bz3_state *state, int stage);
 /* Decode-side kernels that the start-up self-test made the defaults (entropy decoders 8 / 9, the bulk LZP decoder) are
  * backed by the block checksum: a block that fails under them is decoded again with the round-1 kernels, whose verdict
  * the caller gets (so hostile input still yields the reference's error codes, src/libbz3.c:739-809); if the round-1
- * kernels decode it, the newer kernels are retired for the process.  Number of times that happened (0 = never). */
+ * kernels decode it, the newer kernels are retired for the process.  Promoted encode-side kernels are cross-checked
+ * against the round-1 kernels on the first block of every new size class (x2) and retired on a mismatch, the caller
+ * getting the round-1 output.  Number of retirements (0 = never; anything else is a kernel bug worth reporting). */
 BZIP3_API int bz3_b200_demotions(void);
 
 /* The ".bz3" container of the reference's command line tool (src/main.c:157-482: "BZ3v1", s32 LE block size, then per

@@ -346,3 +346,46 @@ def test_a_promoted_decoder_that_errs_is_caught_by_the_block_checksum(emulib):
     assert "NEW 0 3" in text, text
     assert "PINNED -1 %d 1" % bzip3_b200.BZ3_ERR_CRC in text, text
     assert "retired for this process" in text, text
+
+
+def test_a_promoted_encoder_is_cross_checked_once_per_size_class(emulib):
+    """Encode side of the safety net (Probation in bz3_api.cu): the first block of every size class (more than twice the
+    largest size checked so far) is also coded by the round-1 kernel.  A (here: sabotaged) promoted encoder that gets a
+    byte wrong on such a block is caught before the caller sees the block: the round-1 stream is returned, every promoted
+    kernel of the process is retired."""
+    import subprocess
+    import sys
+    script = (
+        "import sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import bzip3_b200\n"
+        "from bzip3_b200 import synth\n"
+        "from tests import refs\n"
+        "bs = %d\n"
+        "def exact(s, data):\n"
+        "    enc, r = s.encode_block(data)\n"
+        "    want = refs.oracle_encode_block(data, bs)\n"
+        "    return r == want[1] and enc == want[0]\n"
+        "with bzip3_b200.Bz3State(bs) as s:\n"
+        "    L = s.L\n"
+        "    print('START', L.bz3_b200_get_variant(s.handle, 105), L.bz3_b200_demotions())\n"
+        "    print('SMALL', exact(s, synth.zipf_text(700, seed=1).tobytes()), L.bz3_b200_demotions(), L.bz3_b200_get_variant(s.handle, 105))\n"
+        "    print('SAMECLASS', exact(s, synth.zipf_text(1300, seed=2).tobytes()), L.bz3_b200_demotions())\n"
+        "    print('CAUGHT', exact(s, synth.zipf_text(1500, seed=3).tobytes()), L.bz3_b200_demotions(), L.bz3_b200_get_variant(s.handle, 105))\n"
+        "    print('AFTER', exact(s, synth.zipf_text(1500, seed=4).tobytes()), L.bz3_b200_demotions())\n"
+        "with bzip3_b200.Bz3State(bs) as t:\n"
+        "    print('NEW', t.L.bz3_b200_get_variant(t.handle, 105), t.L.bz3_b200_get_variant(t.handle, 205), t.L.bz3_b200_get_variant(t.handle, 3))\n" % (ROOT, BS))
+    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="force", BZ3_B200_PROBATION_FROM="0", BZ_EMU_SABOTAGE_ENC_N="1500")
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
+    text = out.stdout + out.stderr
+    assert "START 6 0" in text, text
+    assert "SMALL True 0 6" in text, text          # first block: checked, agrees
+    assert "SAMECLASS True 0" in text, text        # 1300 <= 2 * 700: not checked again
+    assert "CAUGHT True 1 0" in text, text         # 1500 > 2 * 700: checked, the sabotaged stream never reaches the caller
+    assert "AFTER True 1" in text, text
+    assert "NEW 0 0 3" in text, text
+    assert "disagrees with the round-1 kernel" in text, text
+    # without the net the same block comes out wrong -- the hook really bites
+    env2 = dict(env, BZ3_B200_PROBATION_FROM="100000")
+    out = subprocess.run([sys.executable, "-c", script], env=env2, capture_output=True, text=True, timeout=900)
+    assert "CAUGHT False 0 6" in out.stdout, out.stdout + out.stderr
