@@ -1117,7 +1117,7 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     }
     bz3_state* s = new (std::nothrow) bz3_state();
     if (!s) return nullptr;
-    memset(s, 0, sizeof(*s));
+    memset(static_cast<void*>(s), 0, sizeof(*s));   // every field of the state is plain data
     s->block_size = block_size;
     s->device = dev;
     s->last_error = BZ3_OK;

@@ -138,7 +138,7 @@ inline int run(int in_fd, int out_fd, int32_t block_size, int in_flight, bool de
             if (failed) {
                 // after the first error the remaining blocks are only drained
             } else if (S.out_size < 0) {
-                P.fail(S.error ? S.error : BZ3_ERR_INIT);   // blocks before this one are already out, like the reference's loop
+                P.fail(S.error ? (int)S.error : (int)BZ3_ERR_INIT);   // blocks before this one are already out, like the reference's loop
             } else {
                 if (!decode) {
                     uint8_t hdr[8];
