@@ -88,6 +88,10 @@ def lib():
     L.bz3_b200_encode_fd.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_int, u64p, u64p]
     L.bz3_b200_decode_fd.restype = C.c_int
     L.bz3_b200_decode_fd.argtypes = [C.c_int, C.c_int, C.c_int, u64p, u64p]
+    L.bz3_b200_encode_fd2.restype = C.c_int
+    L.bz3_b200_encode_fd2.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_int, C.c_int, u64p, u64p]
+    L.bz3_b200_decode_fd2.restype = C.c_int
+    L.bz3_b200_decode_fd2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, u64p, u64p]
     L.bz3_b200_demotions.restype = C.c_int
     L.bz3_b200_demotions.argtypes = []
     L.bz3_b200_workspace_bytes.restype = C.c_size_t

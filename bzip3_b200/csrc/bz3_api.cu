@@ -1159,6 +1159,8 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
 
 BZIP3_API void bz3_free(struct bz3_state* s) {
     if (!s) return;
+    int caller_device = -1;   // a state may live on another device than the calling thread's current one (bz3_b200_*_fd2)
+    if (cudaGetDevice(&caller_device) != cudaSuccess) caller_device = -1;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int i = 0; i < 3; i++)
@@ -1174,6 +1176,7 @@ BZIP3_API void bz3_free(struct bz3_state* s) {
     for (int i = 0; i < 80; i++)
         if (s->sort_ev[i]) cudaEventDestroy(s->sort_ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (caller_device >= 0 && caller_device != s->device) cudaSetDevice(caller_device);
     delete s;
 }
 
@@ -1544,7 +1547,7 @@ void* stream_host_alloc(size_t n) {
     return p;
 }
 void stream_host_free(void* p) { cudaFreeHost(p); }
-void stream_thread_init(int dev) { cudaSetDevice(dev); }   // the workers' states live on the caller's current device
+void stream_thread_init(int dev) { cudaSetDevice(dev); }   // a worker's state lives on the device the worker was dealt
 int stream_device() {
     int dev = 0;
     return cudaGetDevice(&dev) == cudaSuccess ? dev : 0;
@@ -1572,30 +1575,55 @@ int stream_depth(int32_t block_size, int in_flight) {
 #endif
     return depth < 1 ? 1 : depth;
 }
+
+// Workers are dealt round-robin over `devices` GPUs starting with the caller's current one (1: that one only, the
+// one-process-per-GPU model of bench.py; <= 0: every visible GPU): block i -> worker i mod in_flight -> GPU, the static
+// work queue of SURVEY 8(e) inside one process.  Blocks are independent, so nothing is exchanged between the GPUs.
+std::vector<int> stream_worker_devices(int depth, int devices) {
+    int count = 1;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) count = 1;
+    if (devices <= 0 || devices > count) devices = count;
+    const int first = stream_device();
+    std::vector<int> dev((size_t)depth);
+    for (int k = 0; k < depth; k++) dev[(size_t)k] = (first + k % devices) % count;
+    return dev;
+}
 }  // namespace
 
-BZIP3_API int bz3_b200_encode_fd(int in_fd, int out_fd, int32_t block_size, int in_flight, uint64_t* bytes_in, uint64_t* bytes_out) {
+BZIP3_API int bz3_b200_encode_fd2(int in_fd, int out_fd, int32_t block_size, int in_flight, int devices, uint64_t* bytes_in,
+                                  uint64_t* bytes_out) {
     if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return BZ3_B200_ERR_BLOCK_SIZE;
     u8 head[9] = {'B', 'Z', '3', 'v', '1'};
     put32(head + 5, (u32)block_size);
     if (out_fd >= 0 && !bz3stream::write_full(out_fd, head, 9)) return BZ3_B200_ERR_IO;
     uint64_t out = 0;
-    int r = bz3stream::run(in_fd, out_fd, block_size, stream_depth(block_size, in_flight), false, bytes_in, &out, stream_host_alloc,
-                           stream_host_free, stream_thread_init, stream_device());
+    const int depth = stream_depth(block_size, in_flight);
+    const std::vector<int> dev = stream_worker_devices(depth, devices);
+    int r = bz3stream::run(in_fd, out_fd, block_size, depth, false, bytes_in, &out, stream_host_alloc, stream_host_free,
+                           stream_thread_init, dev.data());
     if (bytes_out) *bytes_out = out + 9;
     return r;
 }
 
-BZIP3_API int bz3_b200_decode_fd(int in_fd, int out_fd, int in_flight, uint64_t* bytes_in, uint64_t* bytes_out) {
+BZIP3_API int bz3_b200_decode_fd2(int in_fd, int out_fd, int in_flight, int devices, uint64_t* bytes_in, uint64_t* bytes_out) {
     u8 head[9];
     if (bz3stream::read_full(in_fd, head, 9) != 9 || memcmp(head, "BZ3v1", 5) != 0) return BZ3_B200_ERR_SIGNATURE;
     const s32 block_size = (s32)get32(head + 5);
     if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return BZ3_B200_ERR_BLOCK_SIZE;
     uint64_t in = 0;
-    int r = bz3stream::run(in_fd, out_fd, block_size, stream_depth(block_size, in_flight), true, &in, bytes_out, stream_host_alloc,
-                           stream_host_free, stream_thread_init, stream_device());
+    const int depth = stream_depth(block_size, in_flight);
+    const std::vector<int> dev = stream_worker_devices(depth, devices);
+    int r = bz3stream::run(in_fd, out_fd, block_size, depth, true, &in, bytes_out, stream_host_alloc, stream_host_free,
+                           stream_thread_init, dev.data());
     if (bytes_in) *bytes_in = in + 9;
     return r;
+}
+
+BZIP3_API int bz3_b200_encode_fd(int in_fd, int out_fd, int32_t block_size, int in_flight, uint64_t* bytes_in, uint64_t* bytes_out) {
+    return bz3_b200_encode_fd2(in_fd, out_fd, block_size, in_flight, 1, bytes_in, bytes_out);
+}
+BZIP3_API int bz3_b200_decode_fd(int in_fd, int out_fd, int in_flight, uint64_t* bytes_in, uint64_t* bytes_out) {
+    return bz3_b200_decode_fd2(in_fd, out_fd, in_flight, 1, bytes_in, bytes_out);
 }
 
 // ------------------------------------------------------------------ single stages on host buffers (tests)

@@ -15,14 +15,15 @@
 #include <cstring>
 #include <string>
 
-typedef int (*enc_fn)(int, int, int32_t, int, uint64_t*, uint64_t*);
-typedef int (*dec_fn)(int, int, int, uint64_t*, uint64_t*);
+typedef int (*enc_fn)(int, int, int32_t, int, int, uint64_t*, uint64_t*);
+typedef int (*dec_fn)(int, int, int, int, uint64_t*, uint64_t*);
 
 static void usage(const char* me) {
     fprintf(stderr,
-            "usage: %s [-e | -d | -t] [-b MiB] [-j blocks-in-flight] [-c] [-f] [-v] [input [output]]\n"
+            "usage: %s [-e | -d | -t] [-b MiB] [-j blocks-in-flight] [-g GPUs] [-c] [-f] [-v] [input [output]]\n"
             "  -e encode (default)   -d decode   -t test      -b block size in MiB (1..511, default 16)\n"
             "  -j blocks in flight on the GPU (default: min(SMs, memory, 64))   -c write to stdout   -f overwrite   -v statistics\n"
+            "  -g number of GPUs the blocks are dealt over (default 1 = the current device, 0 = all visible)\n"
             "  the .bz3 written equals `bzip3 -e -b N`'s byte for byte\n", me);
 }
 
@@ -46,12 +47,13 @@ static const char* why(int rc) {
 }
 
 int main(int argc, char** argv) {
-    int mode = 'e', mib = 16, depth = 0, to_stdout = 0, force = 0, verbose = 0, opt;
-    while ((opt = getopt(argc, argv, "edtb:j:cfvh")) != -1) {
+    int mode = 'e', mib = 16, depth = 0, gpus = 1, to_stdout = 0, force = 0, verbose = 0, opt;
+    while ((opt = getopt(argc, argv, "edtb:j:g:cfvh")) != -1) {
         switch (opt) {
             case 'e': case 'd': case 't': mode = opt; break;
             case 'b': mib = atoi(optarg); break;
             case 'j': depth = atoi(optarg); break;
+            case 'g': gpus = atoi(optarg); break;
             case 'c': to_stdout = 1; break;
             case 'f': force = 1; break;
             case 'v': verbose = 1; break;
@@ -73,8 +75,8 @@ int main(int argc, char** argv) {
     }
     void* h = dlopen(lib.c_str(), RTLD_NOW | RTLD_LOCAL);
     if (!h) { fprintf(stderr, "cannot load %s: %s\n", lib.c_str(), dlerror()); return 1; }
-    enc_fn enc = reinterpret_cast<enc_fn>(dlsym(h, "bz3_b200_encode_fd"));
-    dec_fn dec = reinterpret_cast<dec_fn>(dlsym(h, "bz3_b200_decode_fd"));
+    enc_fn enc = reinterpret_cast<enc_fn>(dlsym(h, "bz3_b200_encode_fd2"));
+    dec_fn dec = reinterpret_cast<dec_fn>(dlsym(h, "bz3_b200_decode_fd2"));
     if (!enc || !dec) { fprintf(stderr, "%s does not export the stream entry points\n", lib.c_str()); return 1; }
 
     int in_fd = 0, out_fd = mode == 't' ? -1 : 1;
@@ -92,7 +94,7 @@ int main(int argc, char** argv) {
     }
     uint64_t nin = 0, nout = 0;
     const auto t0 = std::chrono::steady_clock::now();
-    const int rc = mode == 'e' ? enc(in_fd, out_fd, (int32_t)mib << 20, depth, &nin, &nout) : dec(in_fd, out_fd, depth, &nin, &nout);
+    const int rc = mode == 'e' ? enc(in_fd, out_fd, (int32_t)mib << 20, depth, gpus, &nin, &nout) : dec(in_fd, out_fd, depth, gpus, &nin, &nout);
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc != 0) {
         fprintf(stderr, "Failed to %s: %s (%d)\n", mode == 'e' ? "encode" : "decode", why(rc), rc);

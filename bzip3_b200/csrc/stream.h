@@ -82,11 +82,11 @@ struct Pipe {
 
 typedef void* (*HostAlloc)(size_t);
 typedef void (*HostFree)(void*);
-typedef void (*ThreadInit)(int);   // called first in every worker thread (selects the caller's CUDA device)
+typedef void (*ThreadInit)(int);   // called first in every worker thread with that worker's CUDA device
 
 // Runs the three stages.  `decode`: direction; `out_fd` < 0: test only (nothing written).
 inline int run(int in_fd, int out_fd, int32_t block_size, int in_flight, bool decode, uint64_t* bytes_in, uint64_t* bytes_out,
-               HostAlloc host_alloc, HostFree host_free, ThreadInit thread_init, int thread_arg) {
+               HostAlloc host_alloc, HostFree host_free, ThreadInit thread_init, const int* worker_device) {
     const size_t cap = bz3_bound((size_t)block_size);
     Pipe P;
     P.slot.resize((size_t)in_flight);
@@ -94,7 +94,7 @@ inline int run(int in_fd, int out_fd, int32_t block_size, int in_flight, bool de
 
     auto worker = [&](int k) {
         Slot& S = P.slot[(size_t)k];
-        if (thread_init) thread_init(thread_arg);
+        if (thread_init) thread_init(worker_device[k]);   // block i is coded on the device of worker i mod in_flight
         for (;;) {
             {
                 std::unique_lock<std::mutex> lk(P.m);

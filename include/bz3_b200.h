@@ -92,6 +92,12 @@ BZIP3_API int bz3_b200_demotions(void);
 #define BZ3_B200_ERR_TRUNCATED (-23)  /* file ends inside a block (xread_noeof, :262-270) */
 BZIP3_API int bz3_b200_encode_fd(int in_fd, int out_fd, int32_t block_size, int in_flight, uint64_t *bytes_in, uint64_t *bytes_out);
 BZIP3_API int bz3_b200_decode_fd(int in_fd, int out_fd, int in_flight, uint64_t *bytes_in, uint64_t *bytes_out);
+/* The same over several GPUs of one process: the workers are dealt round-robin over `devices` GPUs starting with the
+ * current one (<= 0: all visible), i.e. block i goes to GPU (i mod in_flight) mod devices -- the static work queue of
+ * independent blocks; nothing is exchanged between GPUs.  in_flight <= 0 then means the automatic depth PER call, so
+ * pass e.g. 64 x devices.  The plain entry points above are devices = 1 (one process per GPU, as bench.py runs). */
+BZIP3_API int bz3_b200_encode_fd2(int in_fd, int out_fd, int32_t block_size, int in_flight, int devices, uint64_t *bytes_in, uint64_t *bytes_out);
+BZIP3_API int bz3_b200_decode_fd2(int in_fd, int out_fd, int in_flight, int devices, uint64_t *bytes_in, uint64_t *bytes_out);
 /* the self-test behind the defaults, run in the calling process on `device` (used by the helper bz3_selftest, which the
  * library spawns so that a misbehaving candidate kernel can never take the caller's CUDA context down); returns 0 and
  * the kernels it would choose */

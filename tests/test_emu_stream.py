@@ -240,3 +240,18 @@ def test_gpu_many_blocks_check_runs_on_the_emulator(L):
     """The body of the GPU test of many blocks in flight (tests/test_gpu_stream.py), at emulator size."""
     from tests.test_gpu_stream import many_blocks_check
     many_blocks_check(L, BS, 6, 1300)
+
+
+def test_dealing_workers_over_devices(L, tmp_path, four_blocks):
+    """bz3_b200_*_fd2 with devices = 0 (all visible: one on the emulator) and more devices than exist."""
+    data, want = four_blocks
+    src, dst = tmp_path / "d.bin", tmp_path / "d.bz3"
+    src.write_bytes(data)
+    for devices in (0, 5):
+        fi, fo = os.open(src, os.O_RDONLY), os.open(dst, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+        try:
+            assert L.bz3_b200_encode_fd2(fi, fo, BS, 3, devices, None, None) == 0
+        finally:
+            os.close(fi)
+            os.close(fo)
+        assert dst.read_bytes() == want

@@ -126,3 +126,15 @@ def test_many_blocks_in_flight_share_two_workspaces():
     """48 states / streams at once (more than the 32 hardware queues), all leasing the device's two stage workspaces:
     bit-exact against the oracle, and the device footprint is 48 small states + 2 workspaces, not 48 workspaces."""
     many_blocks_check(bzip3_b200.lib(), 256 << 10, 48, (256 << 10) - 8)
+
+
+def test_stream_over_all_visible_gpus(tmp_path, corpus):
+    """devices = 0: the workers are dealt over every visible GPU of this process (one GPU on a single-GPU box, where this
+    equals the plain call); the bytes do not depend on where a block was coded."""
+    L = bzip3_b200.lib()
+    data, want = corpus
+    rc, got, _, _ = run_fd(L.bz3_b200_encode_fd2, data, tmp_path, BS, 6, 0)
+    assert rc == 0 and got == want
+    rc, back, _, _ = run_fd(L.bz3_b200_decode_fd2, want, tmp_path, 6, 0)
+    assert rc == 0 and back == data
+    assert L.bz3_b200_demotions() == 0
