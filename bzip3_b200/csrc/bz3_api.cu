@@ -361,6 +361,11 @@ cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* 
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_pf_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     else
         BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+#if defined(BZ_EMU)
+    // test hook of the emulator build (tests/test_emu_library.py): a promoted LZP encoder that gets one byte wrong
+    if (const char* sab = getenv("BZ_EMU_SABOTAGE_LZP_N"))
+        if (lzp_v == 2 && n == atoi(sab)) d_out[9] ^= 0x01;
+#endif
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));   // see run_cm_encode: nothing waits in a queue behind a long kernel

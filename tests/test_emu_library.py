@@ -389,3 +389,30 @@ def test_a_promoted_encoder_is_cross_checked_once_per_size_class(emulib):
     env2 = dict(env, BZ3_B200_PROBATION_FROM="100000")
     out = subprocess.run([sys.executable, "-c", script], env=env2, capture_output=True, text=True, timeout=900)
     assert "CAUGHT False 0 6" in out.stdout, out.stdout + out.stderr
+
+
+def test_a_promoted_lzp_encoder_is_cross_checked_too(emulib):
+    import subprocess
+    import sys
+    script = (
+        "import sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import bzip3_b200\n"
+        "from bzip3_b200 import synth\n"
+        "from tests import refs\n"
+        "bs = %d\n"
+        "line = synth.log_stream(200, seed=3).tobytes()\n"
+        "data = (line * 10)[:1500]\n"
+        "with bzip3_b200.Bz3State(bs) as s:\n"
+        "    L = s.L\n"
+        "    enc, r = s.encode_block(data)\n"
+        "    want = refs.oracle_encode_block(data, bs)\n"
+        "    print('MODEL', want[0][8] & 2, 'EXACT', r == want[1] and enc == want[0], L.bz3_b200_demotions(), L.bz3_b200_get_variant(s.handle, 3))\n" % (ROOT, BS))
+    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="force", BZ3_B200_PROBATION_FROM="0", BZ_EMU_SABOTAGE_LZP_N="1500")
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
+    text = out.stdout + out.stderr
+    assert "MODEL 2 EXACT True 1 3" in text, text       # LZP was in use on this block; caught, round-1 output returned
+    assert "promoted LZP encoder disagrees" in text, text
+    out = subprocess.run([sys.executable, "-c", script], env=dict(env, BZ3_B200_PROBATION_FROM="100000"), capture_output=True,
+                         text=True, timeout=900)
+    assert "EXACT False 0 2" in out.stdout, out.stdout + out.stderr   # without the net the hook bites

@@ -48,6 +48,30 @@ def main():
                     s.decode_block(enc[: len(enc) // 2], len(data))
             print("encoder %d / decoder %d / LZP %d: %d cases round-tripped, no AddressSanitizer report" % (
                 enc_v, dec_v, lzp_v, len(cases)), flush=True)
+    # the file container front end (csrc/stream.h): reader, workers and writer threads on a file of three blocks, whole
+    # and cut short inside a block
+    import ctypes as C
+    import tempfile
+    L = bzip3_b200.lib()
+    line = synth.log_stream(300, seed=5).tobytes()
+    data = (line * (2 * bs // len(line) + 40))[: 2 * bs + 5000]
+    with tempfile.TemporaryDirectory() as tmp:
+        src, dst, back = (os.path.join(tmp, n) for n in ("a", "b", "c"))
+        open(src, "wb").write(data)
+
+        def run(fn, a, b, *args):
+            fi, fo = os.open(a, os.O_RDONLY), os.open(b, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+            try:
+                return fn(fi, fo, *args, None, None)
+            finally:
+                os.close(fi)
+                os.close(fo)
+        assert run(L.bz3_b200_encode_fd, src, dst, bs, 3) == 0
+        assert run(L.bz3_b200_decode_fd, dst, back, 2) == 0 and open(back, "rb").read() == data
+        blob = open(dst, "rb").read()
+        open(dst, "wb").write(blob[: len(blob) - 40])
+        assert run(L.bz3_b200_decode_fd, dst, back, 3) == -23
+    print("container front end: 3 blocks through reader / 3 workers / writer, whole and truncated, no AddressSanitizer report", flush=True)
     print("done")
     return 0
 

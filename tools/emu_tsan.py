@@ -53,6 +53,29 @@ def child(kind, variant):
         ok = ok and all(e == 0 and bytes(b[:len(d)]) == d for d, b, e in zip(datas, bufs, errs))
         for s in states:
             s.close()
+    elif kind == "stream":   # the container front end: reader / `variant` workers / writer threads (csrc/stream.h)
+        import tempfile
+        import bzip3_b200
+        bs = 66 * 1024
+        L = bzip3_b200.lib()
+        line = synth.log_stream(300, seed=5).tobytes()
+        data = (line * (2 * bs // len(line) + 40))[: 2 * bs + 5000]
+        with tempfile.TemporaryDirectory() as tmp:
+            src, dst, back = (os.path.join(tmp, n) for n in ("a", "b", "c"))
+            open(src, "wb").write(data)
+
+            def run(fn, a, b, *args):
+                fi, fo = os.open(a, os.O_RDONLY), os.open(b, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+                try:
+                    return fn(fi, fo, *args, None, None)
+                finally:
+                    os.close(fi)
+                    os.close(fo)
+            ok = run(L.bz3_b200_encode_fd, src, dst, bs, variant) == 0
+            ok = ok and run(L.bz3_b200_decode_fd, dst, back, variant) == 0 and open(back, "rb").read() == data
+            blob = open(dst, "rb").read()
+            open(dst, "wb").write(blob[: len(blob) - 40])
+            ok = ok and run(L.bz3_b200_decode_fd, dst, back, variant) == -23
     elif kind in ("enc", "dec"):
         L = C.CDLL(KSO)
         L.emu_cm_encode.restype = C.c_int32
@@ -126,13 +149,15 @@ def main():
                                         "-lpthread"])
     tsan = subprocess.check_output(["g++", "-print-file-name=libtsan.so"], text=True).strip()
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
-    jobs = [("enc", v) for v in (0, 2, 4, 6)] + [("dec", v) for v in (0, 3, 4, 5, 6, 7, 8, 9)] + [("lzp", 0), ("lzp", 2), ("stages", 0), ("lib", 1), ("lib", 2)]
+    jobs = [("enc", v) for v in (0, 2, 4, 6)] + [("dec", v) for v in (0, 3, 4, 5, 6, 7, 8, 9)] + [("lzp", 0), ("lzp", 2), ("stages", 0), ("lib", 1), ("lib", 2), ("stream", 3)]
     only = os.environ.get("EMU_TSAN_ONLY")   # e.g. EMU_TSAN_ONLY=lib,stages
     jobs = [j for j in jobs if not only or j[0] in only.split(",")]
     bad = 0
     for kind, v in jobs:
         if kind == "lib":
             env = dict(env, BZ3_B200_LIB=LSO, BZ3_B200_ARENAS=str(v), BZ3_B200_AUTOSELECT="0")
+        if kind == "stream":
+            env = dict(env, BZ3_B200_LIB=LSO, BZ3_B200_AUTOSELECT="0")
         out = subprocess.run([sys.executable, os.path.abspath(__file__), kind, str(v)], env=env, capture_output=True, text=True)
         text = out.stdout + out.stderr
         result = "bit-exact" if "RESULT bit-exact" in text else "NO RESULT / WRONG OUTPUT"
@@ -142,7 +167,7 @@ def main():
             key = " <-> ".join(sorted(set(f.strip() for f in fr[:2])))
             races[key] = races.get(key, 0) + 1
         name = {"enc": "CM encoder", "dec": "CM decoder", "lzp": "LZP encoder+decoder variant", "stages": "CRC / mRLE / BWT / inverse BWT",
-                "lib": "library, 4-block batch, workspaces"}[kind]
+                "lib": "library, 4-block batch, workspaces", "stream": "container front end, 3 blocks, workers"}[kind]
         line = "%-30s %d: %s, " % (name, v, result)
         line += "no race reported" if not races else "; ".join("%d x %s" % (c, k) for k, c in races.items())
         print(line, flush=True)
