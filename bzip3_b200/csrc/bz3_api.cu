@@ -1561,12 +1561,14 @@ int stream_device() {
 int stream_depth(int32_t block_size, int in_flight) {
     if (in_flight > 256) in_flight = 256;
     if (in_flight > 0) return in_flight;
-    int depth = 64;   // blocks beyond the SM count only wait; 64 is also where the reference's -j stops (src/main.c:213)
+    int depth = 64;   // fallback if the device cannot be asked
 #if !defined(BZ_EMU)
+    // A block spends most of its time in a single-CTA coder kernel whose tables fill an SM's shared memory: one block per
+    // SM is the useful depth (148 on a B200; the reference's -j stops at 64, src/main.c:213).  Blocks beyond that only wait.
     int dev = 0, sms = 0;
     size_t free_b = 0, total_b = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-        depth = std::min(depth, sms);
+        depth = sms;
     const size_t n = block_bound((size_t)block_size) + 64;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
         const size_t ws = 2 * std::max(sufsort_arena_bytes(n), other_arena_bytes(n)) + (size_t(1) << 30);

@@ -22,7 +22,7 @@ static void usage(const char* me) {
     fprintf(stderr,
             "usage: %s [-e | -d | -t] [-b MiB] [-j blocks-in-flight] [-g GPUs] [-c] [-f] [-v] [input [output]]\n"
             "  -e encode (default)   -d decode   -t test      -b block size in MiB (1..511, default 16)\n"
-            "  -j blocks in flight on the GPU (default: min(SMs, memory, 64))   -c write to stdout   -f overwrite   -v statistics\n"
+            "  -j blocks in flight on the GPU (default: min(SMs, memory))   -c write to stdout   -f overwrite   -v statistics\n"
             "  -g number of GPUs the blocks are dealt over (default 1 = the current device, 0 = all visible)\n"
             "  the .bz3 written equals `bzip3 -e -b N`'s byte for byte\n", me);
 }

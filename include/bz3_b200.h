@@ -82,7 +82,7 @@ BZIP3_API int bz3_b200_demotions(void);
  * block s32 LE coded size, s32 LE original size, coded bytes) over file descriptors, with a deep block queue instead of
  * the reference's read-J / code-J / write-J batches (:352-478, J <= 64): a reader, `in_flight` workers (one state and
  * stream each) and an in-order writer, each running as soon as its slot is ready.  in_flight <= 0 picks
- * min(SM count, what device memory holds, 64).  The bytes written equal `bzip3 -e -b <block_size>`'s.
+ * min(SM count, what device memory and 16 GiB of pinned host buffers hold).  The bytes written equal `bzip3 -e -b <block_size>`'s.
  * decode_fd with out_fd < 0 only tests (`bzip3 -t`).  Return 0, a BZ3_ERR_* of the failing block (blocks before it have
  * been written, as by the reference's loop), or one of the codes below. */
 #define BZ3_B200_ERR_IO (-20)         /* read / write failed */
