@@ -209,7 +209,7 @@ def test_error_paths_wind_the_pipeline_down(L, tmp_path, four_blocks):
 def test_command_line_tool(L, tmp_path):
     """bzip3_b200/bz3b200 (csrc/cli_main.cpp) on the emulator build: same bytes as the reference tool, -d / -t, exit codes."""
     cli = os.path.join(refs.ROOT, "bzip3_b200", "bz3b200")
-    if not os.path.exists(cli):
+    if not (os.path.exists(cli) and os.access(cli, os.X_OK)):
         pytest.skip("bzip3_b200/bz3b200 not built")
     env = dict(os.environ, BZ3_B200_LIB=build_emulated_library(), BZ3_B200_AUTOSELECT="0")
     data = synth.zipf_text(1800, seed=12).tobytes()

@@ -80,7 +80,7 @@ def test_stream_damaged_block(tmp_path, corpus):
 
 def test_command_line_tool(tmp_path, corpus):
     cli = os.path.join(refs.ROOT, "bzip3_b200", "bz3b200")
-    if not os.path.exists(cli):
+    if not (os.path.exists(cli) and os.access(cli, os.X_OK)):
         pytest.skip("bzip3_b200/bz3b200 not built")
     data, want = corpus
     r = subprocess.run([cli, "-e", "-b", "1", "-j", "5"], input=data, capture_output=True, timeout=600)
