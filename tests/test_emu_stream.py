@@ -255,3 +255,70 @@ def test_dealing_workers_over_devices(L, tmp_path, four_blocks):
             os.close(fi)
             os.close(fo)
         assert dst.read_bytes() == want
+
+
+def reference_loop_model(blob, bs):
+    """The decode loop of the reference tool (src/main.c:186-203, :257-278) restated around the oracle's block decoder:
+    returns (code, output) with the codes of include/bz3_b200.h for what the tool reports as text."""
+    if len(blob) < 9 or blob[:5] != b"BZ3v1":
+        return -21, b""
+    block_size = struct.unpack_from("<i", blob, 5)[0]
+    if block_size < 65 * 1024 or block_size > 511 * 1024 * 1024:
+        return -24, b""
+    cap = bzip3_b200.bound(block_size)
+    out = bytearray()
+    at = 9
+    while at < len(blob):
+        if len(blob) - at < 8:
+            return -23, bytes(out)
+        new_size, old_size = struct.unpack_from("<ii", blob, at)
+        if old_size < 0 or new_size < 0 or old_size > cap or new_size > cap:
+            return -22, bytes(out)
+        if len(blob) - at - 8 < new_size:
+            return -23, bytes(out)
+        blk = blob[at + 8: at + 8 + new_size]
+        dec, r, err = refs.oracle_decode_block(blk, old_size, block_size, buffer_size=cap, compressed_size=new_size, err_init=55)
+        if r == -1:
+            return (err if err != 55 else -7), bytes(out)
+        out += dec[:old_size] if len(dec) >= old_size else dec + bytes(old_size - len(dec))
+        at += 8 + new_size
+    return 0, bytes(out)
+
+
+def test_mutated_containers_follow_the_reference_loop(L, tmp_path):
+    """Random damage to a three-block container: same verdict and same bytes out as the reference tool's loop (modelled
+    above around the oracle), whatever gets hit -- signature, block size, block headers, payload, the end of the file."""
+    data = squeezable(2 * BS + 3000, seed=9)
+    good = container(data, BS)
+    assert reference_loop_model(good, BS) == (0, data)
+    rng = np.random.default_rng(2026)
+    offsets = [9]
+    while offsets[-1] < len(good):
+        offsets.append(offsets[-1] + 8 + struct.unpack_from("<i", good, offsets[-1])[0])
+    for trial in range(35):
+        blob = bytearray(good)
+        kind = trial % 7
+        if kind == 0:      # a bit anywhere in a payload
+            k = int(rng.integers(0, len(offsets) - 1))
+            blob[int(rng.integers(offsets[k] + 8, offsets[k + 1]))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:    # a byte of a block header
+            k = int(rng.integers(0, len(offsets) - 1))
+            blob[offsets[k] + int(rng.integers(0, 8))] ^= int(rng.integers(1, 256))
+        elif kind == 2:    # cut anywhere
+            blob = blob[: int(rng.integers(0, len(blob)))]
+        elif kind == 3:    # the first bytes of a block's own header (checksum / BWT index / model)
+            k = int(rng.integers(0, len(offsets) - 1))
+            blob[offsets[k] + 8 + int(rng.integers(0, 9))] ^= int(rng.integers(1, 256))
+        elif kind == 4:    # container header
+            blob[int(rng.integers(0, 9))] ^= int(rng.integers(1, 256))
+        elif kind == 5:    # original size of a block lowered / raised a little
+            k = int(rng.integers(0, len(offsets) - 1))
+            o = struct.unpack_from("<i", blob, offsets[k] + 4)[0]
+            struct.pack_into("<i", blob, offsets[k] + 4, max(0, o + int(rng.integers(-70, 70))))
+        else:              # trailing garbage
+            blob += bytes(rng.integers(0, 256, int(rng.integers(1, 12)), dtype=np.uint8))
+        blob = bytes(blob)
+        want = reference_loop_model(blob, BS)
+        rc, back, _, _ = decode_bytes(L, tmp_path, blob, 1 + trial % 3, name="m%d" % trial)
+        assert rc == want[0], (trial, kind, rc, want[0])
+        assert back == want[1], (trial, kind, len(back), len(want[1]))
