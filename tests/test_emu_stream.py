@@ -319,6 +319,9 @@ def test_mutated_containers_follow_the_reference_loop(L, tmp_path):
             blob += bytes(rng.integers(0, 256, int(rng.integers(1, 12)), dtype=np.uint8))
         blob = bytes(blob)
         want = reference_loop_model(blob, BS)
+        if os.path.exists(refs.REF_CLI):   # the model itself is pinned on the reference binary: exit status and bytes written
+            r = subprocess.run([refs.REF_CLI, "-d"], input=blob, capture_output=True, timeout=120)
+            assert (r.returncode == 0) == (want[0] == 0) and r.stdout == want[1], (trial, kind, r.returncode, want[0])
         rc, back, _, _ = decode_bytes(L, tmp_path, blob, 1 + trial % 3, name="m%d" % trial)
         assert rc == want[0], (trial, kind, rc, want[0])
         assert back == want[1], (trial, kind, len(back), len(want[1]))
