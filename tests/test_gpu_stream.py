@@ -138,3 +138,38 @@ def test_stream_over_all_visible_gpus(tmp_path, corpus):
     rc, back, _, _ = run_fd(L.bz3_b200_decode_fd2, want, tmp_path, 6, 0)
     assert rc == 0 and back == data
     assert L.bz3_b200_demotions() == 0
+
+
+def test_mutated_containers_follow_the_reference_loop(tmp_path, corpus):
+    """Random damage to the container: same verdict and same bytes out as the reference tool's loop (the model of
+    tests/test_emu_stream.py, which is pinned on the reference binary in the CPU suite)."""
+    import numpy as np
+    from tests.test_emu_stream import reference_loop_model
+    L = bzip3_b200.lib()
+    data, good = corpus
+    small = good[: 9]
+    at = 9
+    for _ in range(3):   # the first three blocks are enough: three CPU oracle decodes per trial
+        c = struct.unpack_from("<i", good, at)[0]
+        small += good[at: at + 8 + c]
+        at += 8 + c
+    rng = np.random.default_rng(7)
+    for trial in range(10):
+        blob = bytearray(small)
+        kind = trial % 5
+        if kind == 0:
+            blob[int(rng.integers(30, len(blob)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            blob = blob[: int(rng.integers(9, len(blob)))]
+        elif kind == 2:
+            blob[9 + int(rng.integers(0, 17))] ^= int(rng.integers(1, 256))
+        elif kind == 3:
+            blob[int(rng.integers(0, 9))] ^= int(rng.integers(1, 256))
+        else:
+            blob += bytes(rng.integers(0, 256, int(rng.integers(1, 12)), dtype=np.uint8))
+        blob = bytes(blob)
+        want = reference_loop_model(blob, BS)
+        rc, back, _, _ = run_fd(L.bz3_b200_decode_fd, blob, tmp_path, 1 + trial % 3)
+        assert rc == want[0], (trial, kind, rc, want[0])
+        assert back == want[1], (trial, kind, len(back), len(want[1]))
+    assert L.bz3_b200_demotions() == 0
