@@ -552,7 +552,7 @@ BZ_D void rc_lane3(const u32* __restrict__ pw, const u8* __restrict__ sb, const 
 // Stage s works on chunk it-s in iteration `it`.  A node of depth d is only ever coded at bit position d,
 // so the eight lanes of a stage own disjoint counters and never synchronise with each other.
 template <int MODE>
-__global__ void __launch_bounds__(kCmEncThreads, 1) cm_encode_chunked_kernel(const u8* __restrict__ in, s32 n,
+__global__ void __launch_bounds__(kCmEncThreads, (MODE == 3) ? 1 : 0) cm_encode_chunked_kernel(const u8* __restrict__ in, s32 n,
                                                                          u8* __restrict__ out, s32* out_size) {
     BZ_DYN_SMEM(u16, cm_smem);
     u32* pbuf = reinterpret_cast<u32*>(cm_smem + kCmTableU16);                 // [2][chunk * 8]  P << 14
