@@ -11,10 +11,13 @@
 #if !defined(BZ_EMU) || defined(BZ_EMU_SPAWN_TEST)
 #define BZ_SELFTEST_SPAWN 1
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <poll.h>
 #include <signal.h>
 #include <spawn.h>
+#include <sys/stat.h>
 #include <sys/wait.h>
+#include <time.h>
 #include <unistd.h>
 extern char** environ;
 #endif
@@ -997,6 +1000,31 @@ bool g_selftest_child = false;   // this process IS the helper: test in process
 // selftest_helper.cpp) loads this library, runs selftest_on_device on the same device and prints the choice.  If a
 // candidate kernel hung or crashed there, the helper is killed after a deadline and this process -- whose CUDA
 // context never saw that kernel -- simply keeps the proven kernels.
+// A helper that had to be killed (a candidate kernel hung) costs the whole deadline; the next process on this machine
+// should not pay it again.  A marker file remembers it for an hour: while it is fresh the self-test is skipped and
+// the round-1 kernels stay (BZ3_B200_SELFTEST_MARKER: its path, "" = no marker; default in /tmp, per user and device).
+std::string selftest_marker_path(int device) {
+    if (const char* m = getenv("BZ3_B200_SELFTEST_MARKER")) return m;
+    char name[96];
+    snprintf(name, sizeof name, "/tmp/.bz3_b200_selftest_hung_%u_%d", (unsigned)getuid(), device);
+    return name;
+}
+bool selftest_marker_fresh(int device) {
+    const std::string path = selftest_marker_path(device);
+    struct stat st;
+    if (path.empty() || stat(path.c_str(), &st) != 0) return false;
+    return time(nullptr) - st.st_mtime < 3600;
+}
+void selftest_marker_set(int device) {
+    const std::string path = selftest_marker_path(device);
+    if (path.empty()) return;
+    const int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0600);
+    if (fd >= 0) {
+        if (write(fd, "hung\n", 5) < 0) {}
+        close(fd);
+    }
+}
+
 bool selftest_in_child(int device, KernelChoice& c) {
     Dl_info info;
     if (!dladdr(reinterpret_cast<void*>(&bz3_bound), &info) || !info.dli_fname) return false;
@@ -1020,8 +1048,8 @@ bool selftest_in_child(int device, KernelChoice& c) {
     close(fd[1]);
     if (rc != 0) { close(fd[0]); return false; }
     std::string out;
-    // a fresh box pages the driver in slowly; a hung kernel never ends (BZ3_B200_SELFTEST_TIMEOUT: seconds, for tests)
-    const double deadline = seconds_now() + (double)std::max(1, env_int("BZ3_B200_SELFTEST_TIMEOUT", 90));
+    // a hung kernel never ends; the driver is already paged in by this process's own context (BZ3_B200_SELFTEST_TIMEOUT: seconds)
+    const double deadline = seconds_now() + (double)std::max(1, env_int("BZ3_B200_SELFTEST_TIMEOUT", 45));
     bool eof = false;
     while (!eof) {
         const double left = deadline - seconds_now();
@@ -1036,7 +1064,10 @@ bool selftest_in_child(int device, KernelChoice& c) {
     }
     close(fd[0]);
     int status = 0;
-    if (!eof) kill(pid, SIGKILL);
+    if (!eof) {
+        kill(pid, SIGKILL);
+        selftest_marker_set(device);
+    }
     waitpid(pid, &status, 0);
     if (!eof || !WIFEXITED(status) || WEXITSTATUS(status) != 0) return false;
     int e = -1, d = -1, l = -1;
@@ -1072,7 +1103,9 @@ void kernel_autoselect(bz3_state* s) {
         } else {
 #if defined(BZ_SELFTEST_SPAWN)
             KernelChoice from_child = c;
-            if (selftest_in_child(s->device, from_child)) {
+            if (selftest_marker_fresh(s->device)) {
+                how = "round-1 kernels (a self-test helper had to be killed on this machine within the last hour)";
+            } else if (selftest_in_child(s->device, from_child)) {
                 if (!pin.enc) c.cm_enc = from_child.cm_enc;
                 if (!pin.dec) c.cm_dec = from_child.cm_dec;
                 if (!pin.lzp) c.lzp = from_child.lzp;

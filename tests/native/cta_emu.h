@@ -24,6 +24,9 @@
 #include <sys/mman.h>
 // system headers that product code includes later must come before the CUDA vocabulary macros below (__noinline__ ...)
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <time.h>
 #include <poll.h>
 #include <signal.h>
 #include <spawn.h>

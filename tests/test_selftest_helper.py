@@ -50,8 +50,13 @@ def spawn_dir():
     return DIR
 
 
-def run(extra_env):
-    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_VERBOSE="1")
+MARKER = os.path.join(DIR, "hung.marker")   # the "a helper had to be killed" note, kept out of /tmp for the tests
+
+
+def run(extra_env, keep_marker=False):
+    if not keep_marker and os.path.exists(MARKER):
+        os.remove(MARKER)
+    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_VERBOSE="1", BZ3_B200_SELFTEST_MARKER=MARKER)
     env.update(extra_env)
     out = subprocess.run([sys.executable, "-c", SCRIPT], env=env, capture_output=True, text=True, timeout=600)
     return out.stdout + out.stderr
@@ -101,3 +106,23 @@ def test_pinned_stages_and_switch_off(spawn_dir):
     assert "CHOICE 0 0 3" in text and "self-test off" in text, text
     text = run({"BZ3_B200_CM_ENC": "4", "BZ3_B200_CM_DEC": "5", "BZ3_B200_LZP": "2"})
     assert "CHOICE 4 5 2" in text and "EXACT True" in text, text
+
+
+def test_a_killed_helper_is_remembered(spawn_dir):
+    """A helper that hung costs the deadline once: the next process on the machine sees the marker, skips the self-test and
+    keeps the round-1 kernels; a stale marker (older than an hour) is ignored."""
+    import time
+    install("#!/bin/sh\nexec sleep 100\n")
+    t0 = time.time()
+    text = run({"BZ3_B200_SELFTEST_TIMEOUT": "2"})
+    assert "CHOICE 0 0 3" in text and "did not finish" in text, text
+    assert os.path.exists(MARKER)
+    install()   # even a working helper is not asked while the marker is fresh
+    t0 = time.time()
+    text = run({"BZ3_B200_SELFTEST_TIMEOUT": "60"}, keep_marker=True)
+    assert "CHOICE 0 0 3" in text and "had to be killed on this machine" in text and "EXACT True" in text, text
+    old = time.time() - 7200
+    os.utime(MARKER, (old, old))
+    text = run({}, keep_marker=True)
+    assert "self-test in the helper process" in text, text
+    os.remove(MARKER)
