@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--mib", type=float, default=2.0)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "eval_variants.json"))
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--sets", default="zipf_text,source,mixed")
+    ap.add_argument("--enc", default="0,4,6")
+    ap.add_argument("--dec", default="0,4,6,7,8,9,5")
     args = ap.parse_args()
     n = int(args.mib * (1 << 20))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
@@ -45,6 +48,7 @@ def main():
     u8p = refs.u8p
     sets = [("zipf_text", synth.zipf_text(n, seed=4242)), ("source", synth.source_corpus(n, seed=4243)),
             ("mixed", synth.mixed(n, seed=4244, segment=max(n // 4, 1 << 16)))]
+    sets = [x for x in sets if x[0] in args.sets.split(",")]
     result = {"n": n, "sets": {}, "ok": True}
     with bzip3_b200.Bz3State(max(n, 1 << 20)) as st:
         try:   # what the self-test of the library chose for this process
@@ -77,7 +81,7 @@ def main():
             print("%s: ratio %.3f, oracle on one host core: enc %.1f MB/s, dec %.1f MB/s" % (
                 name, rw / n, n / cpu_enc / 1e6, n / cpu_dec / 1e6), flush=True)
         # known-good kernels first, so that a fault in a new one cannot hide the baseline
-        order = [("enc", 0), ("dec", 0), ("enc", 4), ("dec", 4), ("enc", 6), ("dec", 6), ("dec", 7), ("dec", 8), ("dec", 9), ("dec", 5)]
+        order = [("enc", int(v)) for v in args.enc.split(",") if v] + [("dec", int(v)) for v in args.dec.split(",") if v]
         for kind, v in order:
             for name, _ in sets:
                 bwt, want, rw, cut, dw = prep[name]
