@@ -81,6 +81,8 @@ def lib():
     L.bz3_b200_device_count.restype = C.c_int
     L.bz3_b200_state_device.restype = C.c_int
     L.bz3_b200_state_device.argtypes = [C.c_void_p]
+    L.bz3_b200_set_devices.restype = C.c_int
+    L.bz3_b200_set_devices.argtypes = [C.c_int]
     L.bz3_b200_device_bytes.restype = C.c_size_t
     L.bz3_b200_device_bytes.argtypes = [C.c_void_p]
     u64p = C.POINTER(C.c_uint64)

@@ -40,14 +40,16 @@ extern char** environ;
 #include "sufsort.cuh"
 #include "unbwt.cuh"
 #include "cm.cuh"
+#include "cm_dec.cuh"
+#include "cm_enc.cuh"
 #include "stream.h"
 
 using namespace bz3;
 
-// One stream per block: ask for enough hardware queues that streams do not alias (the default of 8 lets a
-// copy queued behind one block's long coder kernel stall other blocks' launches).  Only effective when the
-// library is loaded before the CUDA context is created; never overrides the user's setting.
-__attribute__((constructor)) static void bz3_b200_env_defaults() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+// One stream per block: with more blocks in flight than hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, default 8) streams
+// alias and a copy queued behind one block's long coder kernel stalls other blocks' launches.  The library does not touch
+// the process environment; bench.py and the bz3b200 tool set CUDA_DEVICE_MAX_CONNECTIONS=32 themselves before the CUDA
+// context exists, and a host program that keeps many blocks in flight should do the same.
 
 #ifndef BZ3_VERSION_STRING
 #define BZ3_VERSION_STRING "1.5.2-b200"
@@ -473,6 +475,8 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
         BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<1>)(d_in, n, d_out, d_res);
     else if (s->cm_enc == 4)
         BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<2>)(d_in, n, d_out, d_res);
+    else if (s->cm_enc == 10)
+        BZ_LAUNCH(1, kCmE2Threads, kCmE2SmemBytes, s->stream, cm_encode_kernel)(d_in, n, d_out, d_res);
     else if (s->cm_enc == 6)
         BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<3>)(d_in, n, d_out, d_res);
     else
@@ -509,6 +513,8 @@ cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s
         BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<1, 0>)(d_in, insize, d_out, n);
     else if (s->cm_dec == 8)
         BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<1, 1>)(d_in, insize, d_out, n);
+    else if (s->cm_dec == 10)
+        BZ_LAUNCH(1, kCmD2Threads, kCmD2SmemBytes, s->stream, cm_decode_kernel)(d_in, insize, d_out, n);
     else if (s->cm_dec == 9)
         BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<2, 1>)(d_in, insize, d_out, n);
     else
@@ -807,6 +813,40 @@ int decode_checked(bz3_state* s, int pay_buf, size_t pay_off, const DecodeHeader
 }
 
 bool use_device(bz3_state* s) { return cudaSetDevice(s->device) == cudaSuccess; }
+
+// Where bz3_new() puts a state.  Default: the calling thread's current device (one process per GPU, as bench.py runs).
+// With BZ3_B200_DEVICES=N|all, or after bz3_b200_set_devices(N), states are dealt round-robin over N visible GPUs
+// starting at the current one: state i -> GPU i mod N -- the reference's "n states, n threads" batch
+// (bz3_encode_blocks, src/libbz3.c:845-856; src/main.c:336-363) then runs block i on GPU i mod N with nothing
+// exchanged between the devices (SURVEY 8b "GPU mapping", 8e).
+std::atomic<int> g_devices{0};        // 0: not decided yet
+std::atomic<unsigned> g_next_device{0};
+int visible_devices() {
+    int n = 0;
+    return (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? n : 0;
+}
+int placement_devices() {
+    int d = g_devices.load();
+    if (d > 0) return d;
+    d = 1;
+    if (const char* v = getenv("BZ3_B200_DEVICES")) {
+        const int vis = visible_devices();
+        d = (v[0] == 'a' || v[0] == 'A') ? vis : atoi(v);
+        d = d < 1 ? 1 : (vis > 0 && d > vis ? vis : d);
+    }
+    g_devices.store(d);
+    return d;
+}
+
+// the calling thread's current device is left as it was found by the entry points of the reference ABI
+struct DeviceScope {
+    int before = -1;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&before) != cudaSuccess) before = -1;
+        if (before != dev) cudaSetDevice(dev); else before = -1;
+    }
+    ~DeviceScope() { if (before >= 0) cudaSetDevice(before); }
+};
 
 }  // namespace
 
@@ -1130,7 +1170,9 @@ void kernel_autoselect(bz3_state* s) {
 bool device_setup(int dev) {
     static std::once_flag once[kMaxDevices];
     static bool good[kMaxDevices];
-    std::call_once(once[dev], [dev] { good[dev] = crc_upload_tables() == cudaSuccess && cm_set_smem_attrs() == cudaSuccess; });
+    std::call_once(once[dev], [dev] { good[dev] = crc_upload_tables() == cudaSuccess && cm_set_smem_attrs() == cudaSuccess &&
+                                           cudaFuncSetAttribute(cm_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmD2SmemBytes) == cudaSuccess &&
+                                           cudaFuncSetAttribute(cm_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmE2SmemBytes) == cudaSuccess; });
     return good[dev];
 }
 
@@ -1153,6 +1195,12 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
         fprintf(stderr, "[bz3_b200] no CUDA device: this library has no CPU path\n");
         return nullptr;
     }
+    if (const int nd = placement_devices(); nd > 1) {   // deal the states over the GPUs (see placement_devices)
+        const int vis = visible_devices();
+        if (vis > 1) dev = (dev + (int)(g_next_device.fetch_add(1) % (unsigned)nd)) % vis;
+        if (dev >= kMaxDevices) dev = 0;
+    }
+    DeviceScope scope(dev);
     bz3_state* s = new (std::nothrow) bz3_state();
     if (!s) return nullptr;
     memset(static_cast<void*>(s), 0, sizeof(*s));   // every field of the state is plain data
@@ -1220,7 +1268,10 @@ BZIP3_API void bz3_free(struct bz3_state* s) {
 
 BZIP3_API size_t bz3_min_memory_needed(int32_t block_size) {  // host-equivalent figure of the reference, :999-1022
     if (block_size < 65 * 1024 || block_size > 511 * 1024 * 1024) return 0;
-    size_t total = 40 /* sizeof(struct bz3_state) in the reference */ + 148992 + 24 /* its cm state */;
+    // sizeof(struct bz3_state) = 48 and sizeof(state) = 149024 in the reference on LP64 (five pointers + s32 + s8,
+    // padded; 148992 bytes of counters + two pointers + four 32-bit fields): checked against the compiled reference
+    // in tests/test_abi.py
+    size_t total = 48 + 149024;
     total += block_bound((size_t)block_size);
     total += (block_bound((size_t)block_size) + 128) * sizeof(s32);
     total += (size_t)kLzpSlots * sizeof(s32);
@@ -1325,6 +1376,7 @@ BZIP3_API int32_t bz3_b200_decode_resident(struct bz3_state* s, int32_t compress
 
 // ------------------------------------------------------------------ reference block API (host buffers)
 BZIP3_API int32_t bz3_encode_block(struct bz3_state* s, uint8_t* buffer, int32_t size) {
+    DeviceScope scope(s->device);
     if (size > s->block_size) { s->last_error = BZ3_ERR_DATA_TOO_BIG; return -1; }
     if (size < 0 || bz3_b200_upload(s, buffer, size) != 0) { s->last_error = BZ3_ERR_INIT; return -1; }
     int32_t r = bz3_b200_encode_resident(s, size);
@@ -1336,6 +1388,7 @@ BZIP3_API int32_t bz3_encode_block(struct bz3_state* s, uint8_t* buffer, int32_t
 
 BZIP3_API int32_t bz3_decode_block(struct bz3_state* s, uint8_t* buffer, size_t buffer_size, int32_t compressed_size,
                                    int32_t orig_size) {
+    DeviceScope scope(s->device);
     if (!use_device(s)) { s->last_error = BZ3_ERR_INIT; return -1; }
     LaunchScope ls(s);
     clocks_begin(s);
@@ -1504,6 +1557,13 @@ BZIP3_API int bz3_b200_device_count(void) {
     return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
 BZIP3_API int bz3_b200_state_device(struct bz3_state* s) { return s->device; }
+BZIP3_API int bz3_b200_set_devices(int devices) {
+    const int vis = visible_devices();
+    int d = devices <= 0 ? vis : devices;
+    d = d < 1 ? 1 : (vis > 0 && d > vis ? vis : d);
+    g_devices.store(d);
+    return d;
+}
 BZIP3_API size_t bz3_b200_device_bytes(struct bz3_state* s) { return s->device_bytes; }
 BZIP3_API size_t bz3_b200_workspace_bytes(struct bz3_state* s) {   // the device's shared stage workspaces, all slots
     ArenaPool& P = g_pool[s->device];

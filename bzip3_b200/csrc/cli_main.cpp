@@ -47,6 +47,8 @@ static const char* why(int rc) {
 }
 
 int main(int argc, char** argv) {
+    // many blocks in flight, one CUDA stream each: ask for enough hardware queues before the CUDA context exists
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int mode = 'e', mib = 16, depth = 0, gpus = 1, to_stdout = 0, force = 0, verbose = 0, opt;
     while ((opt = getopt(argc, argv, "edtb:j:g:cfvh")) != -1) {
         switch (opt) {

@@ -25,6 +25,12 @@ enum {
 /* number of CUDA devices visible / device a state lives on */
 BZIP3_API int bz3_b200_device_count(void);
 BZIP3_API int bz3_b200_state_device(struct bz3_state *state);
+/* Placement of new states.  Default 1: bz3_new() uses the calling thread's current device (one process per GPU).
+ * devices = N (<= 0: all visible): bz3_new() deals states round-robin over N GPUs starting at the current device, so
+ * that the reference's batch calls (bz3_encode_blocks / bz3_decode_blocks with n states, src/libbz3.c:845-870; the
+ * -j loop of src/main.c:336-378) run block i on GPU i mod N.  Same as the environment variable BZ3_B200_DEVICES=N|all.
+ * Returns the number of devices in effect. */
+BZIP3_API int bz3_b200_set_devices(int devices);
 /* device memory a state owns (three block buffers + LZP table) ... */
 BZIP3_API size_t bz3_b200_device_bytes(struct bz3_state *state);
 /* ... and the stage workspaces (mRLE / suffix sort / inverse BWT scratch, 48 B per byte of block) that all states of

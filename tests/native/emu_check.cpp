@@ -6,6 +6,8 @@
 #include "../../bzip3_b200/csrc/common.cuh"
 #include "../../bzip3_b200/csrc/cm.cuh"
 #include "../../bzip3_b200/csrc/lzp_parallel.cuh"
+#include "../../bzip3_b200/csrc/cm_dec.cuh"
+#include "../../bzip3_b200/csrc/cm_enc.cuh"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -37,6 +39,10 @@ EXPORT int32_t emu_cm_encode(int variant, const uint8_t* in, int32_t n, uint8_t*
         case 6:
             b.x = kCmEncThreads;
             emu::launch(g, b, kCmEncSmemBytes, [&] { cm_encode_chunked_kernel<3>(in, n, out, &res); });
+            break;
+        case 10:
+            b.x = kCmE2Threads;
+            emu::launch(g, b, kCmE2SmemBytes, [&] { cm_encode_kernel(in, n, out, &res); });
             break;
         default:
             return -777;
@@ -78,6 +84,10 @@ EXPORT int emu_cm_decode(int variant, const uint8_t* in, int32_t insize, uint8_t
         case 9:
             b.x = kCmDecW6Threads;
             emu::launch(g, b, kCmDecW6SmemBytes, [&] { cm_decode_walkers_kernel<2, 1>(in, insize, out, n); });
+            break;
+        case 10:
+            b.x = kCmD2Threads;
+            emu::launch(g, b, kCmD2SmemBytes, [&] { cm_decode_kernel(in, insize, out, n); });
             break;
         case 5:
             b.x = kCmDecP2Threads;

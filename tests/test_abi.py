@@ -44,9 +44,16 @@ def test_pure_host_helpers(L):
     for n in (0, 1, 49, 50, 1000, 268435456):
         assert L.bz3_bound(n) == n + n // 50 + 32
     assert L.bz3_min_memory_needed(1000) == 0
-    # reference figure for 65 KiB: sizeof(state structs) + bound + 4*(bound+128) + 1 MiB
+    # reference figure (src/libbz3.c:999-1022): sizeof(struct bz3_state) + sizeof(state) + bound + 4*(bound+128) + 1 MiB
     b = 65 * 1024 + 65 * 1024 // 50 + 32
-    assert L.bz3_min_memory_needed(65 * 1024) == 40 + 148992 + 24 + b + 4 * (b + 128) + 4 * (1 << 18)
+    assert L.bz3_min_memory_needed(65 * 1024) == 48 + 149024 + b + 4 * (b + 128) + 4 * (1 << 18)
+    from tests import refs
+    if refs.have_ref():   # the compiled reference itself, when it is there
+        R = refs.ref()
+        R.bz3_min_memory_needed.restype = C.c_size_t
+        R.bz3_min_memory_needed.argtypes = [C.c_int32]
+        for bs in (1000, 65 * 1024, 1 << 20, 16 << 20, 256 << 20, 511 << 20, (511 << 20) + 1):
+            assert L.bz3_min_memory_needed(bs) == R.bz3_min_memory_needed(bs), bs
     assert L.bz3_new(1000) is None  # block size out of range never needs a device
 
 

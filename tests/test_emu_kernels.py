@@ -19,7 +19,7 @@ ROOT = refs.ROOT
 SO = os.path.join(ROOT, "tests", "_build", "libemucheck.so")
 SRCS = [os.path.join(ROOT, "tests", "native", f) for f in ("emu_check.cpp", "cta_emu.cpp")]
 DEPS = SRCS + [os.path.join(ROOT, "tests", "native", "cta_emu.h")] + [
-    os.path.join(ROOT, "bzip3_b200", "csrc", f) for f in ("common.cuh", "cm.cuh", "lzp.cuh", "lzp_parallel.cuh")]
+    os.path.join(ROOT, "bzip3_b200", "csrc", f) for f in ("common.cuh", "cm.cuh", "cm_dec.cuh", "cm_enc.cuh", "lzp.cuh", "lzp_parallel.cuh")]
 
 _lib = None
 
@@ -76,8 +76,8 @@ def cm_inputs():
 CM_CASES = cm_inputs()
 CM_IDS = [c[0] for c in CM_CASES]
 
-ENC_VARIANTS = [0, 1, 2, 4, 6]
-DEC_VARIANTS = [0, 1, 3, 4, 5, 6, 7, 8, 9]
+ENC_VARIANTS = [0, 1, 2, 4, 6, 10]
+DEC_VARIANTS = [0, 1, 3, 4, 5, 6, 7, 8, 9, 10]
 
 
 @pytest.mark.parametrize("variant", ENC_VARIANTS)

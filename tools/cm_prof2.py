@@ -38,13 +38,13 @@ def main():
             L.bz3_b200_stage_bwt(st.handle, data.ctypes.data_as(u8p), n, bwt.ctypes.data_as(u8p))
             enc = np.zeros(2 * n + 64, np.uint8)
             rec = {}
-            for v in (0, 4, 6):
+            for v in [int(x) for x in os.environ.get('BZ3_PROF_ENC', '0,4,6').split(',')]:
                 L.bz3_b200_set_variant(st.handle, CM + 100, v)
                 r = L.bz3_b200_stage_cm_encode(st.handle, bwt.ctypes.data_as(u8p), n, enc.ctypes.data_as(u8p))
                 p = prof()
                 rec["enc_v%d" % v] = {"stage1_busy": p[13] / n, "stage2_busy": p[14] / n, "coder_busy": p[15] / n,
                                       "exact_tier_cycles": p[32] / n, "exact_tier_bytes_frac": p[33] / n}
-            for v in (0, 4, 5, 6, 7, 8, 9):
+            for v in [int(x) for x in os.environ.get('BZ3_PROF_DEC', '0,4,5,6,7,8,9,10').split(',')]:
                 L.bz3_b200_set_variant(st.handle, CM + 200, v)
                 back = np.zeros(n + 8, np.uint8)
                 L.bz3_b200_stage_cm_decode(st.handle, enc.ctypes.data_as(u8p), r, back.ctypes.data_as(u8p), n)
@@ -53,6 +53,9 @@ def main():
                 if v == 0:
                     rec["dec_v0_chain"] = dict(zip(("wait_ptab", "fast_tier", "exact_tier", "publish_wait_byte", "redo_frac"),
                                                    [x / n for x in p[8:13]]))
+                elif v == 10:
+                    rec["dec_v10_walker"] = dict(zip(("first_table", "walk", "publish_wait_spec", "wait_real", "miss_frac"),
+                                                     [x / n for x in p[8:13]]))
                 elif v == 4:
                     rec["dec_v4_chain"] = dict(zip(("wait_ptab", "round1_fast", "round1_exact", "round2_fast", "round2_exact",
                                                     "publish_wait_byte", "fb1_frac", "fb2_frac"), [x / n for x in p[16:24]]))

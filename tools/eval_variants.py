@@ -24,12 +24,14 @@ from tests import refs  # noqa: E402
 
 CM = 5  # BZ3_STAGE_CM
 ENC_VARIANTS = {0: "chunked, select+mul.hi coder lane (round-1 default)", 4: "chunked, one-multiply coder lane, two-tier",
-                6: "chunked, one-multiply coder lane, branch-free byte + resume at first event"}
+                6: "chunked, one-multiply coder lane, branch-free byte + resume at first event",
+                10: "round 2: coder lane with in-place shifts (straight-line byte, second copy after a shift)"}
 DEC_VARIANTS = {0: "tree, serial chain warp (round-1 default)", 3: "all paths, first edition",
                 4: "tree, lane-parallel chain warp", 5: "all paths, one multiply per level",
                 6: "walker warps (all-paths walk) + model threads", 7: "walker warps + slim model threads",
                 8: "walker warps (stop after 3 levels when outside their eighth) + slim model threads",
-                9: "as 8, branch-light parity-unrolled model threads"}
+                9: "as 8, branch-light parity-unrolled model threads",
+                10: "round 2: serial walker with 3-level-deep table prefetch, in-place shifts, named-barrier hand-offs"}
 
 
 def main():
