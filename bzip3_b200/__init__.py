@@ -94,8 +94,6 @@ def lib():
     L.bz3_b200_encode_fd2.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_int, C.c_int, u64p, u64p]
     L.bz3_b200_decode_fd2.restype = C.c_int
     L.bz3_b200_decode_fd2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, u64p, u64p]
-    L.bz3_b200_demotions.restype = C.c_int
-    L.bz3_b200_demotions.argtypes = []
     L.bz3_b200_workspace_bytes.restype = C.c_size_t
     L.bz3_b200_workspace_bytes.argtypes = [C.c_void_p]
     L.bz3_b200_upload.restype = C.c_int
@@ -116,9 +114,6 @@ def lib():
     L.bz3_b200_kernel_launches.restype = C.c_uint64
     L.bz3_b200_kernel_launches.argtypes = [C.c_void_p]
     L.bz3_b200_last_sort_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), _i32p, C.POINTER(C.c_double)]
-    L.bz3_b200_set_variant.argtypes = [C.c_void_p, C.c_int, C.c_int]
-    L.bz3_b200_get_variant.restype = C.c_int
-    L.bz3_b200_get_variant.argtypes = [C.c_void_p, C.c_int]
     L.bz3_b200_stage_crc.restype = C.c_uint32
     L.bz3_b200_stage_crc.argtypes = [C.c_void_p, _u8p, C.c_int32]
     L.bz3_b200_stage_rle_encode.restype = C.c_int32

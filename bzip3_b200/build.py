@@ -8,7 +8,6 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbzip3_b200.so")
-HELPER = os.path.join(HERE, "bz3_selftest")   # spawned by the library for the self-test behind the default kernels
 CLI = os.path.join(HERE, "bz3b200")            # file front end with the deep block queue (csrc/cli_main.cpp)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
@@ -22,7 +21,7 @@ def sources():
 
 
 def stale() -> bool:
-    if not os.path.exists(LIB) or not os.path.exists(HELPER) or not os.path.exists(CLI):
+    if not os.path.exists(LIB) or not os.path.exists(CLI):
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(s) > t for s in sources())
@@ -38,7 +37,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libbzip3_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    subprocess.check_call([os.environ.get("CXX", "g++"), "-O2", "-o", HELPER, os.path.join(CSRC, "selftest_helper.cpp"), "-ldl"])
     subprocess.check_call([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-o", CLI, os.path.join(CSRC, "cli_main.cpp"), "-ldl"])
     return LIB
 

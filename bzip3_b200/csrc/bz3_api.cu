@@ -8,19 +8,6 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
-#if !defined(BZ_EMU) || defined(BZ_EMU_SPAWN_TEST)
-#define BZ_SELFTEST_SPAWN 1
-#include <dlfcn.h>
-#include <fcntl.h>
-#include <poll.h>
-#include <signal.h>
-#include <spawn.h>
-#include <sys/stat.h>
-#include <sys/wait.h>
-#include <time.h>
-#include <unistd.h>
-extern char** environ;
-#endif
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -40,8 +27,6 @@ extern char** environ;
 #include "sufsort.cuh"
 #include "unbwt.cuh"
 #include "cm.cuh"
-#include "cm_dec.cuh"
-#include "cm_enc.cuh"
 #include "stream.h"
 
 using namespace bz3;
@@ -105,11 +90,6 @@ struct bz3_state {
     u64 sort_records;
     s32 sort_rounds;
     double sort_ms;
-    int variant[BZ3_STAGE_COUNT];
-    int cm_enc, cm_dec;   // entropy-stage kernel selection in effect (see kernel_autoselect)
-    int lzp_default;      // LZP kernels used when variant[BZ3_STAGE_LZP] == 0
-    bool enc_promoted, dec_promoted, lzp_promoted;   // cm_enc / cm_dec / lzp_default were put there by the self-test (see
-                                                     // decode_checked and Probation)
     cudaEvent_t sort_ev[2 * 40];
 };
 
@@ -118,10 +98,6 @@ namespace {
 int env_int(const char* name, int fallback) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : fallback;
-}
-bool env_set(const char* name) {
-    const char* v = getenv(name);
-    return v && *v;
 }
 
 // ------------------------------------------------------------------------------- stage workspace pool
@@ -359,18 +335,7 @@ cudaError_t run_rle_decode(bz3_state* s, const u8* d_in, u32 maxin, u8* d_out, u
 cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* result) {
     if (n < kLzpMinMatch + 32) { *result = -1; return cudaSuccess; }
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
-    const int lzp_v = s->variant[BZ3_STAGE_LZP] ? s->variant[BZ3_STAGE_LZP] : s->lzp_default;
-    if (lzp_v == 1)
-        BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_serial_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
-    else if (lzp_v == 2)   // several windows in flight
-        BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_pf_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
-    else
-        BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
-#if defined(BZ_EMU)
-    // test hook of the emulator build (tests/test_emu_library.py): a promoted LZP encoder that gets one byte wrong
-    if (const char* sab = getenv("BZ_EMU_SABOTAGE_LZP_N"))
-        if (lzp_v == 2 && n == atoi(sab)) d_out[9] ^= 0x01;
-#endif
+    BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));   // see run_cm_encode: nothing waits in a queue behind a long kernel
@@ -383,13 +348,7 @@ cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* 
 cudaError_t run_lzp_decode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32 max, s32* result) {
     if (n < 4) { *result = -1; return cudaSuccess; }
     BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
-    const int lzp_v = s->variant[BZ3_STAGE_LZP] ? s->variant[BZ3_STAGE_LZP] : s->lzp_default;
-    if (lzp_v == 1)
-        BZ_LAUNCH(1, 32, 0, s->stream, lzp_decode_serial_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
-    else if (lzp_v == 2)   // bulk decoder
-        BZ_LAUNCH(1, kLzpBulkThreads, 0, s->stream, lzp_decode_bulk_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
-    else
-        BZ_LAUNCH(1, 32, 0, s->stream, lzp_decode_warp_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
+    BZ_LAUNCH(1, kLzpBulkThreads, 0, s->stream, lzp_decode_bulk_kernel)(d_in, n, d_out, max, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));   // see run_cm_encode: nothing waits in a queue behind a long kernel
@@ -444,48 +403,10 @@ cudaError_t run_unbwt(bz3_state* s, const u8* d_in, u32 n, s32 idx, u8* d_out, i
     return unbwt(s->stream, d_in, n, idx, d_out, B, status);
 }
 
-// Entropy-stage kernels.
-//   encoder  0 chunked pipeline, select/mul.hi coder lane        1 single lane (cross-check)
-//            2 chunked, whole-byte exact tier (cross-check)      4 chunked, one-multiply coder lane, two-tier
-//            6 chunked, one-multiply coder lane, branch-free byte + resume at the first event
-//   decoder  0 tree kernel, serial chain warp                    1 single lane (cross-check)
-//            3 all paths, first edition                          4 tree kernel, lane-parallel chain warp
-//            5 all paths, one multiply per level                 6 walker warps (walk of 5) + model threads of 0/4
-//            7 = 6 with the slim model-thread loop               8 = 7, walker warps stop after three levels
-//            9 = 8 with the branch-light, parity-unrolled model-thread loop
-// LZP (BZ3_STAGE_LZP): 0 = the default in effect, 1 single lane, 2 windows in flight / bulk decoder, 3 one window per step.
-// Defaults: see kernel_autoselect(); fixed per process with BZ3_B200_CM_ENC / BZ3_B200_CM_DEC / BZ3_B200_LZP.
-// The defaults are not constants: the first bz3_new() of a process runs a short self-test on the device
-// (kernel_autoselect below) that lets the newer kernels replace the proven ones only if they reproduce the proven
-// kernels' bytes on the test inputs AND are faster there.
-struct KernelChoice {
-    int cm_enc = 0, cm_dec = 0, lzp = 3;   // proven kernels: chunked encoder 0, tree decoder 0, one-window LZP (3)
-    bool enc_promoted = false, dec_promoted = false, lzp_promoted = false;   // chosen by the self-test, not by the user
-};
-KernelChoice g_choice;
-std::once_flag g_choice_once;
-std::mutex g_choice_mutex;          // g_choice after the once-only self-test (demotion, see decode_checked)
-std::atomic<int> g_demotions{0};    // times a promoted decode-side kernel was caught by the block checksum
-
+// Entropy stage: one thread block per block of data (cm.cuh).
 cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* out_size) {
     s32* d_res = reinterpret_cast<s32*>(s->d_scal + 12);
-    if (s->cm_enc == 1)
-        BZ_LAUNCH(1, kCmThreads, kCmSmemBytes, s->stream, cm_encode_single_kernel)(d_in, n, d_out, d_res);
-    else if (s->cm_enc == 2)
-        BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<1>)(d_in, n, d_out, d_res);
-    else if (s->cm_enc == 4)
-        BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<2>)(d_in, n, d_out, d_res);
-    else if (s->cm_enc == 10)
-        BZ_LAUNCH(1, kCmE2Threads, kCmE2SmemBytes, s->stream, cm_encode_kernel)(d_in, n, d_out, d_res);
-    else if (s->cm_enc == 6)
-        BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<3>)(d_in, n, d_out, d_res);
-    else
-        BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_chunked_kernel<0>)(d_in, n, d_out, d_res);
-#if defined(BZ_EMU)
-    // test hook of the emulator build (tests/test_emu_library.py): a promoted encoder that gets one byte wrong
-    if (const char* sab = getenv("BZ_EMU_SABOTAGE_ENC_N"))
-        if (s->cm_enc >= 4 && n == atoi(sab)) d_out[5] ^= 0x08;
-#endif
+    BZ_LAUNCH(1, kCmEncThreads, kCmEncSmemBytes, s->stream, cm_encode_kernel)(d_in, n, d_out, d_res);
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     // Nothing is queued behind a long single-CTA kernel: with more streams than hardware queues (32 at most,
@@ -499,98 +420,10 @@ cudaError_t run_cm_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* o
 }
 
 cudaError_t run_cm_decode(bz3_state* s, const u8* d_in, s32 insize, u8* d_out, s32 n) {
-    if (s->cm_dec == 1)
-        BZ_LAUNCH(1, kCmThreads, kCmSmemBytes, s->stream, cm_decode_single_kernel)(d_in, insize, d_out, n);
-    else if (s->cm_dec == 3)
-        BZ_LAUNCH(1, kCmDecPathsThreads, kCmDecSmemBytes, s->stream, cm_decode_paths_kernel)(d_in, insize, d_out, n);
-    else if (s->cm_dec == 4)
-        BZ_LAUNCH(1, kCmDecThreads, kCmDecLanesSmemBytes, s->stream, cm_decode_lanes_kernel)(d_in, insize, d_out, n);
-    else if (s->cm_dec == 5)
-        BZ_LAUNCH(1, kCmDecP2Threads, kCmDecP2SmemBytes, s->stream, cm_decode_paths2_kernel)(d_in, insize, d_out, n);
-    else if (s->cm_dec == 6)
-        BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<0, 0>)(d_in, insize, d_out, n);
-    else if (s->cm_dec == 7)
-        BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<1, 0>)(d_in, insize, d_out, n);
-    else if (s->cm_dec == 8)
-        BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<1, 1>)(d_in, insize, d_out, n);
-    else if (s->cm_dec == 10)
-        BZ_LAUNCH(1, kCmD2Threads, kCmD2SmemBytes, s->stream, cm_decode_kernel)(d_in, insize, d_out, n);
-    else if (s->cm_dec == 9)
-        BZ_LAUNCH(1, kCmDecW6Threads, kCmDecW6SmemBytes, s->stream, cm_decode_walkers_kernel<2, 1>)(d_in, insize, d_out, n);
-    else
-        BZ_LAUNCH(1, kCmDecThreads, kCmDecSmemBytes, s->stream, cm_decode_tree_kernel)(d_in, insize, d_out, n);
-#if defined(BZ_EMU)
-    // test hook of the emulator build (tests/test_emu_library.py): a promoted decoder that gets one byte wrong
-    if (const char* sab = getenv("BZ_EMU_SABOTAGE_DEC_N"))
-        if (s->cm_dec >= 4 && n == atoi(sab) && n > 0) d_out[n / 2] ^= 0x20;
-#endif
+    BZ_LAUNCH(1, kCmDecThreads, kCmDecSmemBytes, s->stream, cm_decode_kernel)(d_in, insize, d_out, n);
     BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     return cudaStreamSynchronize(s->stream);   // see run_cm_encode: the inverse BWT's launches must not queue behind the decoder
-}
-
-// ---------------------------------------------------------------------------------- promoted kernels on probation
-// Kernels that the start-up self-test made the defaults have been compared with the round-1 kernels on 48 KiB inputs,
-// nothing larger.  Two nets keep a kernel bug that only shows on real blocks from reaching the caller: the decode side
-// is covered by the block checksum (decode_checked below); the encode side, where a wrong byte would be silent data
-// loss, by Probation: the first block of every new size class (more than twice the largest size checked so far) is
-// ALSO coded by the round-1 kernel and the outputs compared; blocks of that class arriving meanwhile wait for the
-// verdict.  So a process pays the round-1 kernel once per doubling of its block size (in the warm-up of any
-// benchmark), and a mismatch retires every promoted kernel of the process and hands the round-1 output to the caller.
-void retire_promoted_kernels(bz3_state* s) {
-    s->cm_enc = s->enc_promoted ? 0 : s->cm_enc;
-    s->cm_dec = s->dec_promoted ? 0 : s->cm_dec;
-    s->lzp_default = s->lzp_promoted ? 3 : s->lzp_default;
-    s->enc_promoted = s->dec_promoted = s->lzp_promoted = false;
-}
-
-void retire_everywhere(bz3_state* s, const char* what) {
-    if (g_demotions.fetch_add(1) == 0)
-        fprintf(stderr, "[bz3_b200] WARNING: %s; the newer kernels are retired for this process (please report)\n", what);
-    {
-        std::lock_guard<std::mutex> lk(g_choice_mutex);
-        g_choice.cm_enc = g_choice.enc_promoted ? 0 : g_choice.cm_enc;
-        g_choice.cm_dec = g_choice.dec_promoted ? 0 : g_choice.cm_dec;
-        g_choice.lzp = g_choice.lzp_promoted ? 3 : g_choice.lzp;
-        g_choice.enc_promoted = g_choice.dec_promoted = g_choice.lzp_promoted = false;
-    }
-    retire_promoted_kernels(s);
-}
-
-constexpr s64 kSelfTestBytes = 48 * 1024;
-
-struct Probation {
-    std::mutex m;
-    std::condition_variable cv;
-    s64 verified = -1;   // largest size on which the promoted kernel matched the round-1 kernel (-1: not initialised)
-    bool busy = false;
-    // true: the caller must cross-check this block (and call end()); false: go ahead (possibly after the kernels were retired)
-    bool begin(s64 n) {
-        std::unique_lock<std::mutex> lk(m);
-        if (verified < 0) verified = env_set("BZ3_B200_PROBATION_FROM") ? env_int("BZ3_B200_PROBATION_FROM", 0) : kSelfTestBytes;
-        cv.wait(lk, [&] { return !busy || n <= 2 * verified || g_demotions.load() > 0; });
-        if (n <= 2 * verified || g_demotions.load() > 0) return false;
-        busy = true;
-        return true;
-    }
-    void end(s64 n, bool same) {
-        {
-            std::lock_guard<std::mutex> lk(m);
-            busy = false;
-            if (same && n > verified) verified = n;
-        }
-        cv.notify_all();
-    }
-};
-Probation g_probation_enc, g_probation_lzp;
-
-bool device_bytes_equal(bz3_state* s, const u8* a, const u8* b, size_t n) {
-    std::vector<u8> ha(n), hb(n);
-    if (n == 0) return true;
-    if (cudaMemcpyAsync(ha.data(), a, n, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
-        cudaMemcpyAsync(hb.data(), b, n, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess)
-        return false;
-    return memcmp(ha.data(), hb.data(), n) == 0;
 }
 
 // ---------------------------------------------------------------------------------- block encode
@@ -605,7 +438,6 @@ struct EncodeResult {
 int encode_core(bz3_state* s, int in_buf, s32 size, EncodeResult& R) {
     int cur = in_buf, other = (in_buf + 1) % 3, third = (in_buf + 2) % 3;
     s32 cur_size = size;
-    if (g_demotions.load() > 0) retire_promoted_kernels(s);
     R.model = 0;
     R.lzp_size = R.rle_size = -1;
     {
@@ -623,26 +455,7 @@ int encode_core(bz3_state* s, int in_buf, s32 size, EncodeResult& R) {
     }
     {
         Timer t(s, BZ3_STAGE_LZP);
-        const bool lzp_cand = s->lzp_promoted && s->variant[BZ3_STAGE_LZP] == 0 && s->lzp_default != 3;
-        const bool check = lzp_cand && g_probation_lzp.begin(cur_size);
-        if (g_demotions.load() > 0) retire_promoted_kernels(s);   // the verdict waited for may have been "retire"
-        cudaError_t err = run_lzp_encode(s, s->d_buf[cur], cur_size, s->d_buf[other], &R.lzp_size);
-        if (check) {   // once per size class: the round-1 kernel codes the block too (into the buffer free at this stage)
-            s32 z0 = -1;
-            const int v = s->lzp_default;
-            s->lzp_default = 3;
-            if (err == cudaSuccess) err = run_lzp_encode(s, s->d_buf[cur], cur_size, s->d_buf[third], &z0);
-            s->lzp_default = v;
-            const bool same = err == cudaSuccess && z0 == R.lzp_size &&
-                              (z0 <= 0 || device_bytes_equal(s, s->d_buf[other], s->d_buf[third], (size_t)z0));
-            if (err == cudaSuccess && !same) {
-                retire_everywhere(s, "the promoted LZP encoder disagrees with the round-1 kernel on a block");
-                R.lzp_size = z0;
-                if (z0 > 0) err = cudaMemcpyAsync(s->d_buf[other], s->d_buf[third], (size_t)z0, cudaMemcpyDeviceToDevice, s->stream);
-            }
-            g_probation_lzp.end(cur_size, same);
-        }
-        if (err != cudaSuccess) return BZ3_ERR_INIT;
+        if (run_lzp_encode(s, s->d_buf[cur], cur_size, s->d_buf[other], &R.lzp_size) != cudaSuccess) return BZ3_ERR_INIT;
     }
     if (R.lzp_size > 0 && R.lzp_size < cur_size) {  // :617
         int t = cur; cur = other; other = t;
@@ -657,26 +470,7 @@ int encode_core(bz3_state* s, int in_buf, s32 size, EncodeResult& R) {
     R.payload_buf = third;
     {
         Timer t(s, BZ3_STAGE_CM);
-        const bool enc_cand = s->enc_promoted && s->cm_enc != 0;
-        const bool check = enc_cand && g_probation_enc.begin(cur_size);
-        if (g_demotions.load() > 0) retire_promoted_kernels(s);
-        cudaError_t err = run_cm_encode(s, s->d_buf[other], cur_size, s->d_buf[third], &R.payload);
-        if (check) {   // the BWT's input buffer is free by now: the round-1 encoder's stream goes there
-            s32 p0 = -1;
-            const int v = s->cm_enc;
-            s->cm_enc = 0;
-            if (err == cudaSuccess) err = run_cm_encode(s, s->d_buf[other], cur_size, s->d_buf[cur], &p0);
-            s->cm_enc = v;
-            const bool same = err == cudaSuccess && p0 == R.payload && p0 > 0 &&
-                              device_bytes_equal(s, s->d_buf[cur], s->d_buf[third], (size_t)p0);
-            if (err == cudaSuccess && !same) {
-                retire_everywhere(s, "the promoted entropy encoder disagrees with the round-1 kernel on a block");
-                R.payload = p0;
-                R.payload_buf = cur;
-            }
-            g_probation_enc.end(cur_size, same);
-        }
-        if (err != cudaSuccess) return BZ3_ERR_INIT;
+        if (run_cm_encode(s, s->d_buf[other], cur_size, s->d_buf[third], &R.payload) != cudaSuccess) return BZ3_ERR_INIT;
     }
     return BZ3_OK;
 }
@@ -781,37 +575,6 @@ int decode_core(bz3_state* s, int pay_buf, size_t pay_off, const DecodeHeader& H
     return BZ3_OK;
 }
 
-// decode_core with a second opinion.  The newer decode-side kernels (entropy decoders 8 / 9, bulk LZP decoder) become
-// defaults on the strength of the start-up self-test alone.  Every block carries a checksum, so a block that fails
-// under such a promoted kernel -- wrong checksum or any other error -- is decoded once more with the round-1 kernels
-// (the payload buffer is never written by the stages, so it is still there).  Their verdict is what the caller gets,
-// which keeps the error behaviour the reference's on hostile input; and if THEY decode the block, the promoted
-// kernel was wrong: it is retired for the whole process, counted (bz3_b200_demotions) and reported on stderr.
-// Kernels the user selected (bz3_b200_set_variant, BZ3_B200_CM_DEC / BZ3_B200_LZP) get no second opinion: they are
-// what is being tested.
-int decode_checked(bz3_state* s, int pay_buf, size_t pay_off, const DecodeHeader& H, size_t buffer_size, s32 orig_size,
-                   int* out_buf, s32* out_size, bool* crc_ok) {
-    if (g_demotions.load() > 0) retire_promoted_kernels(s);
-    const bool dec_cand = s->dec_promoted && s->cm_dec != 0;
-    const bool lzp_cand = s->lzp_promoted && s->variant[BZ3_STAGE_LZP] == 0 && s->lzp_default != 3 && (H.model & 2);
-    int e = decode_core(s, pay_buf, pay_off, H, buffer_size, orig_size, out_buf, out_size, crc_ok);
-    if ((e == BZ3_OK && *crc_ok) || !(dec_cand || lzp_cand)) return e;
-    const int dec0 = s->cm_dec, lzp0 = s->lzp_default;
-    s->cm_dec = dec_cand ? 0 : dec0;
-    s->lzp_default = lzp_cand ? 3 : lzp0;
-    *crc_ok = false;
-    e = decode_core(s, pay_buf, pay_off, H, buffer_size, orig_size, out_buf, out_size, crc_ok);
-    if (e == BZ3_OK && *crc_ok) {   // the block was fine, the promoted kernel was not
-        char what[160];
-        snprintf(what, sizeof what, "a block that failed with entropy decoder %d / LZP %d decodes with the round-1 kernels", dec0, lzp0);
-        retire_everywhere(s, what);
-    } else {                        // the input is bad: both kernels say so, the promoted ones stay
-        s->cm_dec = dec0;
-        s->lzp_default = lzp0;
-    }
-    return e;
-}
-
 bool use_device(bz3_state* s) { return cudaSetDevice(s->device) == cudaSuccess; }
 
 // Where bz3_new() puts a state.  Default: the calling thread's current device (one process per GPU, as bench.py runs).
@@ -873,296 +636,7 @@ BZIP3_API const char* bz3_strerror(struct bz3_state* state) {  // reference src/
     }
 }
 
-// ------------------------------------------------------------------ choice of the default kernels
-// Runs once per process, on the first state, before the state is handed to the caller.  The proven kernels
-// (entropy encoder 0 / decoder 0, one-window LZP) are the reference: a newer kernel becomes the default only if it
-// reproduces their bytes on every test input -- full and truncated streams -- and needs less time there.
-// Environment: BZ3_B200_CM_ENC / BZ3_B200_CM_DEC / BZ3_B200_LZP pin a stage; BZ3_B200_AUTOSELECT=0 keeps the proven
-// kernels, =force accepts a newer kernel that is correct without asking the clock (emulator, experiments).
 namespace {
-
-void selftest_bytes(u8* p, s32 n, u32 seed) {   // deterministic input with runs, skewed symbols and a noisy stretch
-    u32 x = seed * 2654435761u + 12345u;
-    s32 i = 0;
-    while (i < n) {
-        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
-        const u32 kind = x & 7u;
-        u8 sym = (kind < 5) ? (u8)("etaoin shrdlu"[(x >> 8) % 13]) : (u8)(x >> 16);
-        s32 run = (kind == 0) ? (s32)((x >> 24) & 63u) + 1 : (kind < 3 ? (s32)((x >> 24) & 3u) + 1 : 1);
-        if (i > n / 2 && i < n / 2 + n / 8) { sym = (u8)(x >> 9); run = 1; }   // incompressible stretch
-        while (run-- > 0 && i < n) p[i++] = sym;
-    }
-}
-
-double seconds_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-
-struct SelfTest {
-    bz3_state* s;
-    std::vector<u8> a, b;   // host staging
-    bool h2d(const u8* h, u8* d, size_t n) {
-        return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s->stream) == cudaSuccess && cudaStreamSynchronize(s->stream) == cudaSuccess;
-    }
-    bool d2h(u8* h, const u8* d, size_t n) {
-        return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess && cudaStreamSynchronize(s->stream) == cudaSuccess;
-    }
-    // entropy encoder `v` on d_buf[0][0..n) -> d_buf[1]; returns size (<0 on failure), bytes in `out`, best time of two
-    s32 cm_encode(int v, s32 n, std::vector<u8>& out, double& best) {
-        s->cm_enc = v;
-        s32 size = -1;
-        best = 1e30;
-        for (int rep = 0; rep < 2; rep++) {
-            const double t0 = seconds_now();
-            if (run_cm_encode(s, s->d_buf[0], n, s->d_buf[1], &size) != cudaSuccess || size <= 0 || (size_t)size > s->cap) return -1;
-            best = std::min(best, seconds_now() - t0);
-        }
-        out.assign((size_t)size, 0);
-        return d2h(out.data(), s->d_buf[1], (size_t)size) ? size : -1;
-    }
-    // entropy decoder `v` on d_buf[1][0..insize) -> d_buf[2][0..n)
-    bool cm_decode(int v, s32 insize, s32 n, std::vector<u8>& out, double& best) {
-        s->cm_dec = v;
-        best = 1e30;
-        for (int rep = 0; rep < 2; rep++) {
-            const double t0 = seconds_now();
-            if (run_cm_decode(s, s->d_buf[1], insize, s->d_buf[2], n) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) return false;
-            best = std::min(best, seconds_now() - t0);
-        }
-        out.assign((size_t)n, 0);
-        return d2h(out.data(), s->d_buf[2], (size_t)n);
-    }
-};
-
-struct Pins {
-    bool enc, dec, lzp;
-};
-
-// The device part of the self-test: returns the kernels to use, starting from `c` (proven kernels + pins).
-KernelChoice selftest_on_device(bz3_state* s, KernelChoice c, const bool force, const Pins pin) {
-    const bool pin_enc = pin.enc, pin_dec = pin.dec, pin_lzp = pin.lzp;
-    {
-#if defined(BZ_EMU)
-        const s32 n = 3000;    // the CPU emulator codes a few kilobytes per second
-#else
-        const s32 n = 48 * 1024;
-#endif
-        constexpr int kNewEnc = 6, kNewLzp = 2;
-        SelfTest T{s};
-        std::vector<u8> x((size_t)n + 64, 0), ref, cand, back;
-        selftest_bytes(x.data(), n, 20260923u);
-        double t_ref = 0, t_new = 0;
-        // ---- entropy stage
-        s32 r0 = -1;
-        if (T.h2d(x.data(), s->d_buf[0], (size_t)n + 64)) r0 = T.cm_encode(0, n, ref, t_ref);
-        bool base_ok = r0 > 0 && T.cm_decode(0, r0, n, back, t_new) && memcmp(back.data(), x.data(), (size_t)n) == 0;
-        if (base_ok && !pin_enc) {
-            const s32 r1 = T.cm_encode(kNewEnc, n, cand, t_new);
-            if (r1 == r0 && memcmp(cand.data(), ref.data(), (size_t)r0) == 0 && (force || t_new < 0.9 * t_ref)) c.cm_enc = kNewEnc;
-            T.h2d(ref.data(), s->d_buf[1], (size_t)r0);   // the decoders below read the proven encoder's stream
-        }
-        if (base_ok && !pin_dec) {
-            std::vector<u8> full0, cut0a, cut0b, full1, cut1;
-            double t0d = 0, tt = 0;
-            // truncated streams: the decoders must agree on the garbage as well (read_in() past the end, src/libbz3.c:345)
-            bool ok0 = T.cm_decode(0, r0 / 2, n, cut0a, tt) && T.cm_decode(0, 5, n, cut0b, tt) && T.cm_decode(0, r0, n, full0, t0d) &&
-                       memcmp(full0.data(), x.data(), (size_t)n) == 0;
-            double best = 0.9 * t0d;
-            for (int v : {8, 9}) {   // walker kernels: slim model threads / branch-light model threads
-                double t1d = 0;
-                bool ok = ok0 && T.cm_decode(v, r0 / 2, n, cut1, tt) && cut1 == cut0a && T.cm_decode(v, 5, n, cut1, tt) && cut1 == cut0b &&
-                          T.cm_decode(v, r0, n, full1, t1d) && full1 == full0;
-                if (ok && (t1d < best || (force && c.cm_dec == 0))) {
-                    c.cm_dec = v;
-                    best = std::min(best, t1d);
-                }
-            }
-        }
-        // ---- LZP: an input with long matches, escapes and literal stretches
-        if (!pin_lzp) {
-            std::vector<u8> y((size_t)n + 64, 0);
-            selftest_bytes(y.data(), n, 777u);
-            for (s32 i = n / 3; i + 600 < n; i += 1700) memcpy(y.data() + i, y.data() + i / 4, 600);   // repeats
-            for (s32 i = 50; i < n; i += 997) y[(size_t)i] = (u8)kLzpEscape;
-            std::vector<u8> e0, e1, d0, d1;
-            s32 z0 = -2, z1 = -2, w0 = -2, w1 = -2;
-            double te0 = 1e30, te1 = 1e30, td0 = 1e30, td1 = 1e30;
-            bool ok = true;
-            for (int v : {3, kNewLzp}) {
-                s->lzp_default = v;
-                s32& z = (v == 3) ? z0 : z1;
-                double& te = (v == 3) ? te0 : te1;
-                std::vector<u8>& e = (v == 3) ? e0 : e1;
-                for (int rep = 0; rep < 2 && ok; rep++) {
-                    ok = T.h2d(y.data(), s->d_buf[0], (size_t)n + 64);
-                    const double t0 = seconds_now();
-                    ok = ok && run_lzp_encode(s, s->d_buf[0], n, s->d_buf[1], &z) == cudaSuccess;
-                    te = std::min(te, seconds_now() - t0);
-                }
-                if (ok && z > 0 && (size_t)z <= s->cap) { e.assign((size_t)z, 0); ok = T.d2h(e.data(), s->d_buf[1], (size_t)z); }
-            }
-            ok = ok && z0 == z1 && e0 == e1;
-            if (ok && z0 > 0) {
-                for (int v : {3, kNewLzp}) {
-                    s->lzp_default = v;
-                    s32& w = (v == 3) ? w0 : w1;
-                    double& td = (v == 3) ? td0 : td1;
-                    std::vector<u8>& d = (v == 3) ? d0 : d1;
-                    for (int rep = 0; rep < 2 && ok; rep++) {
-                        ok = T.h2d(e0.data(), s->d_buf[1], (size_t)z0);
-                        const double t0 = seconds_now();
-                        ok = ok && run_lzp_decode(s, s->d_buf[1], z0, s->d_buf[2], n + 32, &w) == cudaSuccess;
-                        td = std::min(td, seconds_now() - t0);
-                    }
-                    if (ok && w > 0) { d.assign((size_t)w, 0); ok = T.d2h(d.data(), s->d_buf[2], (size_t)w); }
-                }
-                ok = ok && w0 == n && w1 == n && d0 == d1 && memcmp(d0.data(), y.data(), (size_t)n) == 0;
-                // truncated token stream: same verdict
-                s32 c0 = -2, c1 = -2;
-                s->lzp_default = 3;
-                ok = ok && T.h2d(e0.data(), s->d_buf[1], (size_t)z0) && run_lzp_decode(s, s->d_buf[1], z0 / 2, s->d_buf[2], n + 32, &c0) == cudaSuccess;
-                s->lzp_default = kNewLzp;
-                ok = ok && T.h2d(e0.data(), s->d_buf[1], (size_t)z0) && run_lzp_decode(s, s->d_buf[1], z0 / 2, s->d_buf[2], n + 32, &c1) == cudaSuccess;
-                ok = ok && c0 == c1;
-            } else {
-                ok = false;
-            }
-            if (ok && (force || te1 + td1 < 0.9 * (te0 + td0))) c.lzp = kNewLzp;
-        }
-        cudaStreamSynchronize(s->stream);
-        s->launches = 0;
-    }
-    return c;
-}
-
-bool g_selftest_child = false;   // this process IS the helper: test in process
-
-#if defined(BZ_SELFTEST_SPAWN)
-// The candidates have to prove themselves in ANOTHER process first: bzip3_b200/bz3_selftest (a few lines, see
-// selftest_helper.cpp) loads this library, runs selftest_on_device on the same device and prints the choice.  If a
-// candidate kernel hung or crashed there, the helper is killed after a deadline and this process -- whose CUDA
-// context never saw that kernel -- simply keeps the proven kernels.
-// A helper that had to be killed (a candidate kernel hung) costs the whole deadline; the next process on this machine
-// should not pay it again.  A marker file remembers it for an hour: while it is fresh the self-test is skipped and
-// the round-1 kernels stay (BZ3_B200_SELFTEST_MARKER: its path, "" = no marker; default in /tmp, per user and device).
-std::string selftest_marker_path(int device) {
-    if (const char* m = getenv("BZ3_B200_SELFTEST_MARKER")) return m;
-    char name[96];
-    snprintf(name, sizeof name, "/tmp/.bz3_b200_selftest_hung_%u_%d", (unsigned)getuid(), device);
-    return name;
-}
-bool selftest_marker_fresh(int device) {
-    const std::string path = selftest_marker_path(device);
-    struct stat st;
-    if (path.empty() || stat(path.c_str(), &st) != 0) return false;
-    return time(nullptr) - st.st_mtime < 3600;
-}
-void selftest_marker_set(int device) {
-    const std::string path = selftest_marker_path(device);
-    if (path.empty()) return;
-    const int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0600);
-    if (fd >= 0) {
-        if (write(fd, "hung\n", 5) < 0) {}
-        close(fd);
-    }
-}
-
-bool selftest_in_child(int device, KernelChoice& c) {
-    Dl_info info;
-    if (!dladdr(reinterpret_cast<void*>(&bz3_bound), &info) || !info.dli_fname) return false;
-    std::string lib = info.dli_fname;
-    const size_t slash = lib.rfind('/');
-    std::string helper = (slash == std::string::npos ? std::string(".") : lib.substr(0, slash)) + "/bz3_selftest";
-    if (access(helper.c_str(), X_OK) != 0) return false;
-    int fd[2];
-    if (pipe(fd) != 0) return false;
-    posix_spawn_file_actions_t fa;
-    posix_spawn_file_actions_init(&fa);
-    posix_spawn_file_actions_adddup2(&fa, fd[1], 1);
-    posix_spawn_file_actions_addclose(&fa, fd[0]);
-    posix_spawn_file_actions_addclose(&fa, fd[1]);
-    char dev[16];
-    snprintf(dev, sizeof dev, "%d", device);
-    char* argv[] = {const_cast<char*>(helper.c_str()), const_cast<char*>(lib.c_str()), dev, nullptr};
-    pid_t pid = 0;
-    const int rc = posix_spawn(&pid, helper.c_str(), &fa, nullptr, argv, environ);
-    posix_spawn_file_actions_destroy(&fa);
-    close(fd[1]);
-    if (rc != 0) { close(fd[0]); return false; }
-    std::string out;
-    // a hung kernel never ends; the driver is already paged in by this process's own context (BZ3_B200_SELFTEST_TIMEOUT: seconds)
-    const double deadline = seconds_now() + (double)std::max(1, env_int("BZ3_B200_SELFTEST_TIMEOUT", 45));
-    bool eof = false;
-    while (!eof) {
-        const double left = deadline - seconds_now();
-        if (left <= 0) break;
-        struct pollfd pf = {fd[0], POLLIN, 0};
-        const int pr = poll(&pf, 1, (int)(left * 1000.0) + 1);
-        if (pr < 0) break;
-        if (pr == 0) continue;
-        char buf[256];
-        const ssize_t got = read(fd[0], buf, sizeof buf);
-        if (got <= 0) eof = true; else out.append(buf, (size_t)got);
-    }
-    close(fd[0]);
-    int status = 0;
-    if (!eof) {
-        kill(pid, SIGKILL);
-        selftest_marker_set(device);
-    }
-    waitpid(pid, &status, 0);
-    if (!eof || !WIFEXITED(status) || WEXITSTATUS(status) != 0) return false;
-    int e = -1, d = -1, l = -1;
-    const size_t at = out.find("BZ3SELFTEST");
-    if (at == std::string::npos || sscanf(out.c_str() + at, "BZ3SELFTEST %d %d %d", &e, &d, &l) != 3) return false;
-    if ((e != 0 && e != 6) || (d != 0 && d != 8 && d != 9) || (l != 3 && l != 2)) return false;
-    c.cm_enc = e;
-    c.cm_dec = d;
-    c.lzp = l;
-    return true;
-}
-#endif
-
-void kernel_autoselect(bz3_state* s) {
-    KernelChoice c;   // the proven kernels
-    const char* mode = getenv("BZ3_B200_AUTOSELECT");
-    const bool off = mode && mode[0] == '0';
-    const bool force = mode && mode[0] == 'f';
-    const Pins pin = {env_set("BZ3_B200_CM_ENC"), env_set("BZ3_B200_CM_DEC"), env_set("BZ3_B200_LZP")};
-    if (pin.enc) c.cm_enc = env_int("BZ3_B200_CM_ENC", 0);
-    if (pin.dec) c.cm_dec = env_int("BZ3_B200_CM_DEC", 0);
-    if (pin.lzp) c.lzp = env_int("BZ3_B200_LZP", 3);
-    const char* how = "round-1 kernels (self-test off)";
-    if (!off && !(pin.enc && pin.dec && pin.lzp)) {
-#if defined(BZ_SELFTEST_SPAWN)
-        const bool in_process = g_selftest_child || force || (mode && mode[0] == 'i');
-#else
-        const bool in_process = true;   // plain emulator build: no helper
-#endif
-        if (in_process) {
-            c = selftest_on_device(s, c, force, pin);
-            how = "self-test in this process";
-        } else {
-#if defined(BZ_SELFTEST_SPAWN)
-            KernelChoice from_child = c;
-            if (selftest_marker_fresh(s->device)) {
-                how = "round-1 kernels (a self-test helper had to be killed on this machine within the last hour)";
-            } else if (selftest_in_child(s->device, from_child)) {
-                if (!pin.enc) c.cm_enc = from_child.cm_enc;
-                if (!pin.dec) c.cm_dec = from_child.cm_dec;
-                if (!pin.lzp) c.lzp = from_child.lzp;
-                how = "self-test in the helper process";
-            } else {
-                how = "round-1 kernels (the self-test helper was not available or did not finish)";
-            }
-#endif
-        }
-    }
-    c.enc_promoted = !pin.enc && c.cm_enc != 0;
-    c.dec_promoted = !pin.dec && c.cm_dec != 0;
-    c.lzp_promoted = !pin.lzp && c.lzp != 3;
-    g_choice = c;
-    if (getenv("BZ3_B200_VERBOSE"))
-        fprintf(stderr, "[bz3_b200] kernels in effect: entropy encoder %d, decoder %d, LZP %d -- %s\n", c.cm_enc, c.cm_dec, c.lzp, how);
-}
 
 // Per-device constants (CRC tables in constant memory, the kernels' shared-memory opt-in): once per device, not once per
 // state -- states are also created while other blocks are running (stream.h), and there is no reason to rewrite a
@@ -1170,20 +644,8 @@ void kernel_autoselect(bz3_state* s) {
 bool device_setup(int dev) {
     static std::once_flag once[kMaxDevices];
     static bool good[kMaxDevices];
-    std::call_once(once[dev], [dev] { good[dev] = crc_upload_tables() == cudaSuccess && cm_set_smem_attrs() == cudaSuccess &&
-                                           cudaFuncSetAttribute(cm_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmD2SmemBytes) == cudaSuccess &&
-                                           cudaFuncSetAttribute(cm_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCmE2SmemBytes) == cudaSuccess; });
+    std::call_once(once[dev], [dev] { good[dev] = crc_upload_tables() == cudaSuccess && cm_set_smem_attrs() == cudaSuccess; });
     return good[dev];
-}
-
-void apply_default_kernels(bz3_state* s) {
-    std::lock_guard<std::mutex> lk(g_choice_mutex);
-    s->cm_enc = g_choice.cm_enc;
-    s->cm_dec = g_choice.cm_dec;
-    s->lzp_default = g_choice.lzp;
-    s->enc_promoted = g_choice.enc_promoted;
-    s->dec_promoted = g_choice.dec_promoted;
-    s->lzp_promoted = g_choice.lzp_promoted;
 }
 
 }  // namespace
@@ -1207,9 +669,6 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
     s->block_size = block_size;
     s->device = dev;
     s->last_error = BZ3_OK;
-    s->cm_enc = 0;
-    s->cm_dec = 0;
-    s->lzp_default = 3;
     const size_t n = block_bound((size_t)block_size) + 64;
     s->cap = align_up(n + 256);
     bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -1238,8 +697,6 @@ BZIP3_API struct bz3_state* bz3_new(int32_t block_size) {
         bz3_free(s);
         return nullptr;
     }
-    std::call_once(g_choice_once, kernel_autoselect, s);
-    apply_default_kernels(s);
     return s;
 }
 
@@ -1364,7 +821,7 @@ BZIP3_API int32_t bz3_b200_decode_resident(struct bz3_state* s, int32_t compress
     int ob = in_buf;
     s32 osz = 0;
     bool crc_ok = false;
-    int e = decode_checked(s, in_buf, (size_t)H.hdr, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
+    int e = decode_core(s, in_buf, (size_t)H.hdr, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
     clocks_collect(s, 1);
     if (e != BZ3_OK) { s->last_error = (s8)e; return -1; }
     s->resident_buf = ob;
@@ -1420,7 +877,7 @@ BZIP3_API int32_t bz3_decode_block(struct bz3_state* s, uint8_t* buffer, size_t 
     int ob = 0;
     s32 osz = 0;
     bool crc_ok = false;
-    int e = decode_checked(s, 0, 0, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
+    int e = decode_core(s, 0, 0, H, buffer_size, orig_size, &ob, &osz, &crc_ok);
     if (e != BZ3_OK) { s->last_error = (s8)e; clocks_collect(s, 1); return -1; }
     s->last_error = BZ3_OK;
     {
@@ -1594,49 +1051,6 @@ extern "C" BZIP3_API void bz3_b200_debug_cm_profile(unsigned long long* out16) {
     cudaMemcpyFromSymbol(out16, g_cm_prof, sizeof(unsigned long long) * 48);
 }
 #endif
-// What the self-test chooses on `device`, computed in THIS process (entry point of bzip3_b200/bz3_selftest).
-BZIP3_API int bz3_b200_selftest(int device, int* cm_enc, int* cm_dec, int* lzp) {
-    g_selftest_child = true;
-    if (cudaSetDevice(device) != cudaSuccess) return 2;
-    bz3_state* s = bz3_new(65 * 1024);
-    if (!s) return 3;
-    *cm_enc = g_choice.cm_enc;
-    *cm_dec = g_choice.cm_dec;
-    *lzp = g_choice.lzp;
-    bz3_free(s);
-    return 0;
-}
-BZIP3_API int bz3_b200_get_variant(struct bz3_state* s, int stage) {
-    if (stage == BZ3_STAGE_CM + 100) return s->cm_enc;
-    if (stage == BZ3_STAGE_CM + 200) return s->cm_dec;
-    if (stage == BZ3_STAGE_LZP) return s->variant[stage] ? s->variant[stage] : s->lzp_default;
-    return (stage >= 0 && stage < BZ3_STAGE_COUNT) ? s->variant[stage] : -1;
-}
-BZIP3_API void bz3_b200_set_variant(struct bz3_state* s, int stage, int variant) {
-    if (stage >= 0 && stage < BZ3_STAGE_COUNT) s->variant[stage] = variant;
-    // the entropy stage has separate encoder / decoder selections: BZ3_STAGE_CM sets both (0 = defaults),
-    // BZ3_STAGE_CM + 100 the encoder alone, BZ3_STAGE_CM + 200 the decoder alone
-    if (stage == BZ3_STAGE_CM) {
-        const int lzp_keep = s->lzp_default;
-        const bool lzp_flag = s->lzp_promoted;
-        apply_default_kernels(s);
-        s->lzp_default = lzp_keep;
-        s->lzp_promoted = lzp_flag;
-        if (variant) {
-            s->cm_enc = s->cm_dec = variant;
-            s->enc_promoted = s->dec_promoted = false;   // the user's choice: no second opinion (decode_checked, Probation)
-        }
-    } else if (stage == BZ3_STAGE_CM + 100) {
-        s->cm_enc = variant;
-        s->enc_promoted = false;
-    } else if (stage == BZ3_STAGE_CM + 200) {
-        s->cm_dec = variant;
-        s->dec_promoted = false;
-    }
-}
-
-BZIP3_API int bz3_b200_demotions(void) { return g_demotions.load(); }
-
 // ------------------------------------------------------------------ the CLI's container with a deep block queue (stream.h)
 namespace {
 void* stream_host_alloc(size_t n) {

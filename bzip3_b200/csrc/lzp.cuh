@@ -132,13 +132,5 @@ BZ_HD s32 lzp_decode_serial(const u8* in, s32 n, u8* out, s32 max, s32* lut) {
     return op;
 }
 
-#if defined(BZ_DEVICE_CODE)
-__global__ void lzp_encode_serial_kernel(const u8* in, s32 n, u8* out, s32* lut, s32* result) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *result = lzp_encode_serial(in, n, out, lut);
-}
-__global__ void lzp_decode_serial_kernel(const u8* in, s32 n, u8* out, s32 max, s32* lut, s32* result) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *result = lzp_decode_serial(in, n, out, max, lut);
-}
-#endif
 
 }  // namespace bz3

@@ -136,302 +136,6 @@ __global__ void __launch_bounds__(32) lzp_encode_warp_kernel(const u8* __restric
     if (lane == 0) *result = op >= out_stop ? -1 : op;
 }
 
-// ---- encoder with several windows in flight (variant 2) -----------------------------------------------------
-// Measured on B200: the windowed encoder above takes ~1700 cycles per window of 32 positions, which is two
-// dependent L2 round trips (table probe, then the quick-check words at the probed position) and little else.
-// This version reads the table and the quick-check words for kLzpPf consecutive windows at once and then
-// commits the windows in order exactly as before.  What the sequential algorithm would have read can differ from
-// the early read only if an earlier window OF THE SAME GROUP wrote that table slot; a bitmap of the 2^18 slots
-// in shared memory (32 KiB) records the slots written by the group, and a lane whose slot is marked (or whose
-// predecessor is a lower lane of its own window) simply reads again at commit time.  A match ends the group
-// (the positions behind it shift).  The tail of the block and everything near scan_end run on the one-window
-// path, which is the kernel above verbatim.
-constexpr int kLzpPf = 8;
-
-struct LzpEncState {
-    s32 ip, op, veto_until;
-};
-
-// Commits one window.  `ref`, `ra`, `rb` are what the lane read early (table entry and the words at ref+36 / ref),
-// `pa`, `pb` the words of its own position; `fresh` tells whether the early read is still what the sequential
-// algorithm would see (slot not written since).  Returns true when a match was taken.
-BZ_D bool lzp_encode_commit_window(const u8* __restrict__ in, u8* __restrict__ out, s32* __restrict__ lut, u32* dirty,
-                                   const s32 W, const bool phase0, const s32 scan_end, const s32 out_stop, const u32 lane,
-                                   const u32 lt, const u32 h, s32 ref, const u32 pa, const u32 pb, u32 ra, u32 rb,
-                                   bool fresh, LzpEncState& S, bool& stored) {
-    const s32 ip = S.ip;
-    const bool active = (s32)lane < W;
-    const s32 p = ip + (s32)lane;
-    const u8 b = (u8)(pb & 0xFFu);
-    const u32 peers = __match_any_sync(kFullMask, h);
-    const u32 lower = peers & lt;
-    if (active && dirty && !lower) fresh = fresh && !((dirty[h >> 5] >> (h & 31u)) & 1u);
-    const bool redo = active && (lower != 0u || !fresh);
-    if (__any_sync(kFullMask, redo)) {
-        if (redo) {
-            // the nearest lower lane with the same hash wrote the slot last; otherwise read the table again
-            ref = lower ? ip + (31 - __clz((int)lower)) : __ldcg(&lut[h]);
-            if (phase0 && ref > 0) {
-                ra = lzp_ld32(in + ref + kLzpMinMatch - 4);
-                rb = lzp_ld32(in + ref);
-            }
-        }
-    }
-    s32 match_lane = -1, mlen = 0;
-    if (phase0) {
-        const bool qc = active && ref > 0 && pa == ra && pb == rb;
-        u32 cand = __ballot_sync(kFullMask, qc);
-        while (cand) {
-            const int l = __ffs((int)cand) - 1;
-            cand &= cand - 1;
-            const s32 pl = ip + l;
-            const s32 rl = __shfl_sync(kFullMask, ref, l);
-            if (S.veto_until > pl && lzp_ld32(in + S.veto_until) != lzp_ld32(in + rl + (S.veto_until - pl))) continue;
-            s32 len = lzp_warp_match_words(in, pl, rl, scan_end, lane);
-            if (len < kLzpMinMatch) {
-                if (S.veto_until < pl + len) S.veto_until = pl + len;
-                continue;
-            }
-            len += in[pl + len] == in[rl + len];
-            len += in[pl + len] == in[rl + len];
-            len += in[pl + len] == in[rl + len];
-            match_lane = l;
-            mlen = len;
-            break;
-        }
-    }
-    // positions ip .. ip+nvis-1 are visited (the match start included): they own their table slot
-    const s32 nvis = match_lane >= 0 ? match_lane + 1 : W;
-    const bool visited = (s32)lane < nvis;
-    const u32 vis_peers = peers & __ballot_sync(kFullMask, visited);
-    stored = visited && (31 - __clz((int)vis_peers)) == (int)lane;   // last visited lane of a hash wins
-    if (stored) {
-        __stcg(&lut[h], p);
-        if (dirty) atomicOr(&dirty[h >> 5], 1u << (h & 31u));
-    }
-    // literals: lanes below the match (or the whole window); an escape byte with a live slot takes two bytes
-    const s32 nlit = match_lane >= 0 ? match_lane : W;
-    const bool lit = (s32)lane < nlit;
-    const bool esc = lit && b == kLzpEscape && ref > 0;
-    const u32 escm = __ballot_sync(kFullMask, esc);
-    if (lit) {
-        u8* o = out + S.op + lane + __popc(escm & lt);
-        o[0] = b;
-        if (esc) o[1] = 255;
-    }
-    S.op += nlit + __popc(escm);
-    if (match_lane >= 0) {
-        s32 o = S.op;
-        if (lane == 0) {
-            out[o++] = (u8)kLzpEscape;
-            s32 code = mlen - kLzpMinMatch;
-            while (code >= 254) {
-                code -= 254;
-                out[o++] = 254;
-                if (o >= out_stop) break;
-            }
-            out[o++] = (u8)code;
-        }
-        S.op = __shfl_sync(kFullMask, o, 0);
-        S.ip += match_lane + mlen;
-    } else {
-        S.ip += W;
-    }
-    __syncwarp();
-    return match_lane >= 0;
-}
-
-__global__ void __launch_bounds__(32) lzp_encode_warp_pf_kernel(const u8* __restrict__ in, s32 n, u8* __restrict__ out,
-                                                                s32* __restrict__ lut, s32* __restrict__ result) {
-    __shared__ u32 dirty[kLzpSlots / 32];
-    const u32 lane = lane_id();
-    const u32 lt = lanemask_lt();
-    if (n < kLzpMinMatch + 32) {
-        if (lane == 0) *result = -1;
-        return;
-    }
-    for (int k = lane; k < kLzpSlots / 32; k += 32) dirty[k] = 0;
-    __syncwarp();
-    const s32 out_stop = n - 8;
-    const s32 scan_end = n - kLzpMinMatch - 32;
-    if (lane < 4) out[lane] = in[lane];
-    LzpEncState S;
-    S.ip = 4;
-    S.op = 4;
-    S.veto_until = 0;
-    // groups of kLzpPf full windows
-    while (S.ip + 32 * kLzpPf <= scan_end && S.op < out_stop) {
-        u32 h[kLzpPf], pa[kLzpPf], pb[kLzpPf], ra[kLzpPf], rb[kLzpPf];
-        s32 ref[kLzpPf];
-#pragma unroll
-        for (int k = 0; k < kLzpPf; k++) {
-            const s32 p = S.ip + 32 * k + (s32)lane;
-            h[k] = lzp_hash(lzp_context(in, p));
-            ref[k] = __ldcg(&lut[h[k]]);
-            pb[k] = lzp_ld32(in + p);
-            pa[k] = lzp_ld32(in + p + kLzpMinMatch - 4);
-        }
-#pragma unroll
-        for (int k = 0; k < kLzpPf; k++) {
-            ra[k] = 0;
-            rb[k] = 0;
-            if (ref[k] > 0) {
-                ra[k] = lzp_ld32(in + ref[k] + kLzpMinMatch - 4);
-                rb[k] = lzp_ld32(in + ref[k]);
-            }
-        }
-        u32 mine = 0;   // bit k: this lane marked its slot of window k
-        bool stop = false;
-#pragma unroll
-        for (int k = 0; k < kLzpPf; k++) {
-            if (!stop) {
-                bool stored;
-                const bool matched = lzp_encode_commit_window(in, out, lut, dirty, 32, true, scan_end, out_stop, lane, lt, h[k],
-                                                              ref[k], pa[k], pb[k], ra[k], rb[k], true, S, stored);
-                if (stored) mine |= 1u << k;
-                stop = matched || S.op >= out_stop;   // uniform
-            }
-        }
-        // unmark the slots of this group
-#pragma unroll
-        for (int k = 0; k < kLzpPf; k++)
-            if ((mine >> k) & 1u) atomicAnd(&dirty[h[k] >> 5], ~(1u << (h[k] & 31u)));
-        __syncwarp();
-    }
-    // the rest: one window at a time (phase 0: positions that may start a match; phase 1: literal-only tail)
-    for (int phase = 0; phase < 2; phase++) {
-        const s32 limit = phase == 0 ? scan_end : n;
-        while (S.ip < limit && S.op < out_stop) {
-            const s32 W = (limit - S.ip) < 32 ? (limit - S.ip) : 32;
-            const bool active = (s32)lane < W;
-            const s32 p = S.ip + (s32)lane;
-            u32 hh = 0xFFFFFFFFu - lane;  // inactive lanes never collide
-            s32 rf = 0;
-            u32 wa = 0, wb = 0, xa = 0, xb = 0;
-            if (active) {
-                hh = lzp_hash(lzp_context(in, p));
-                rf = __ldcg(&lut[hh]);
-                wb = in[p];
-                if (phase == 0) {
-                    wb = lzp_ld32(in + p);
-                    wa = lzp_ld32(in + p + kLzpMinMatch - 4);
-                    if (rf > 0) {
-                        xa = lzp_ld32(in + rf + kLzpMinMatch - 4);
-                        xb = lzp_ld32(in + rf);
-                    }
-                }
-            }
-            bool stored;
-            lzp_encode_commit_window(in, out, lut, nullptr, W, phase == 0, scan_end, out_stop, lane, lt, hh, rf, wa, wb, xa, xb,
-                                     true, S, stored);
-        }
-    }
-    if (lane == 0) *result = S.op >= out_stop ? -1 : S.op;
-}
-
-__global__ void __launch_bounds__(32) lzp_decode_warp_kernel(const u8* __restrict__ in, s32 n, u8* __restrict__ out,
-                                                             s32 max, s32* __restrict__ lut, s32* __restrict__ result) {
-    const u32 lane = lane_id();
-    if (n < 4) {
-        if (lane == 0) *result = -1;
-        return;
-    }
-    if (lane < 4) out[lane] = in[lane];
-    s32 ip = 4, op = 4;
-    // the four most recent output bytes, most recent in the low byte (uniform across the warp)
-    u32 tail = (u32)in[3] | ((u32)in[2] << 8) | ((u32)in[1] << 16) | ((u32)in[0] << 24);
-    s32 status = 0;
-    while (ip < n && op < max) {
-        s32 W = n - ip;
-        if (max - op < W) W = max - op;
-        if (W > 32) W = 32;
-        const bool active = (s32)lane < W;
-        const u32 b = active ? (u32)in[ip + lane] : 0u;
-        const u32 escmask = __ballot_sync(kFullMask, active && b == (u32)kLzpEscape);
-        const s32 nlit = escmask ? (__ffs(escmask) - 1) : W;
-        // context of lane l = output bytes op+l-4 .. op+l-1: lower lanes' bytes, or the carried tail
-        const u32 b1 = __shfl_up_sync(kFullMask, b, 1), b2 = __shfl_up_sync(kFullMask, b, 2);
-        const u32 b3 = __shfl_up_sync(kFullMask, b, 3), b4 = __shfl_up_sync(kFullMask, b, 4);
-        u32 ctx;
-        {
-            // byte j-1-lane of `tail` is the output byte j positions before op+lane when lane < j
-            const u32 c1 = lane >= 1 ? b1 : (tail >> (8 * ((0 - lane) & 3))) & 0xFF;
-            const u32 c2 = lane >= 2 ? b2 : (tail >> (8 * ((1 - lane) & 3))) & 0xFF;
-            const u32 c3 = lane >= 3 ? b3 : (tail >> (8 * ((2 - lane) & 3))) & 0xFF;
-            const u32 c4 = lane >= 4 ? b4 : (tail >> (8 * ((3 - lane) & 3))) & 0xFF;
-            ctx = c1 | (c2 << 8) | (c3 << 16) | (c4 << 24);
-        }
-        if ((s32)lane < nlit) {
-            out[op + lane] = (u8)b;
-            atomicMax(&lut[lzp_hash(ctx)], op + (s32)lane);  // visited positions only grow
-        }
-        // new tail after nlit literals (uniform): bytes at op+nlit-1 .. op+nlit-4
-        if (nlit > 0) {
-            u32 nt = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int src = nlit - 1 - k;  // lane holding the k-th most recent byte, or the old tail
-                const u32 v = __shfl_sync(kFullMask, b, src < 0 ? 0 : src);
-                const u32 byte = src >= 0 ? v : (tail >> (8 * ((-src - 1) & 3))) & 0xFF;
-                nt |= byte << (8 * k);
-            }
-            tail = nt;
-        }
-        op += nlit;
-        ip += nlit;
-        __syncwarp();
-        if (!(escmask && nlit < W)) continue;
-        // ---- the byte at `ip` is 0xF2: resolve it against the table (all lanes run this uniformly)
-        s32 ref = 0;
-        if (lane == 0) {
-            // earlier atomicMax updates of this warp must be visible: same-thread ordering does not cover
-            // other lanes, so go through the L2 with an atomic exchange-like max
-            ref = atomicMax(&lut[lzp_hash(tail)], op);
-        }
-        ref = __shfl_sync(kFullMask, ref, 0);
-        if (ref <= 0) {  // empty slot: 0xF2 is an ordinary literal (src/libbz3.c:212, :236)
-            if (lane == 0) out[op] = (u8)kLzpEscape;
-            tail = (tail << 8) | (u32)kLzpEscape;
-            op++;
-            ip++;
-            continue;
-        }
-        ip++;
-        if (ip == n) { status = -1; break; }
-        u32 c = in[ip];
-        if (c == 255) {  // escaped literal
-            ip++;
-            if (lane == 0) out[op] = (u8)kLzpEscape;
-            tail = (tail << 8) | (u32)kLzpEscape;
-            op++;
-            continue;
-        }
-        u32 ulen = kLzpMinMatch;  // wraps like the reference's signed 32-bit accumulator
-        bool truncated = false;
-        for (;;) {
-            if (ip == n) { truncated = true; break; }
-            c = in[ip++];
-            ulen += c;
-            if (c != 254) break;
-        }
-        if (truncated) { status = -1; break; }
-        s64 stop64 = (s64)op + (s64)(s32)ulen;
-        if (stop64 > max) stop64 = max;
-        const s32 count = stop64 > op ? (s32)(stop64 - op) : 0;
-        if (count > 0) {
-            __threadfence_block();
-            const s32 dist = op - ref;  // > 0; the source [ref, op) is final, the copy repeats it with period dist
-            for (s32 k = lane; k < count; k += 32) out[op + k] = __ldcg(out + ref + (dist >= count ? k : k % dist));
-            __threadfence_block();
-            __syncwarp();
-            op += count;
-            tail = (u32)__ldcg(out + op - 1) | ((u32)__ldcg(out + op - 2) << 8) | ((u32)__ldcg(out + op - 3) << 16) |
-                   ((u32)__ldcg(out + op - 4) << 24);
-        }
-    }
-    if (lane == 0) *result = status < 0 ? -1 : op;
-}
-
 // ---- bulk decoder (variant 2) --------------------------------------------------------------------------------
 // The sequential decoder reads the table only when the input byte is 0xF2; everything between two such bytes
 // is a run of literals whose only side effect is  table[hash(context)] = position  for every position -- and

@@ -70,20 +70,6 @@ BZIP3_API int32_t bz3_b200_stage_unbwt(struct bz3_state *state, const uint8_t *i
 BZIP3_API int32_t bz3_b200_stage_cm_encode(struct bz3_state *state, const uint8_t *in, int32_t n, uint8_t *out);
 BZIP3_API int bz3_b200_stage_cm_decode(struct bz3_state *state, const uint8_t *in, int32_t insize, uint8_t *out,
                                        int32_t n);
-/* implementation selectors for stages that have more than one kernel form (0 = the default in effect: what the
- * self-test of the first bz3_new() of the process chose, or what BZ3_B200_CM_ENC / BZ3_B200_CM_DEC / BZ3_B200_LZP
- * pin).  The entropy stage selects encoder and decoder kernels separately: stage BZ3_STAGE_CM sets both,
- * BZ3_STAGE_CM + 100 the encoder, BZ3_STAGE_CM + 200 the decoder.  get_variant reports the selection in effect. */
-BZIP3_API void bz3_b200_set_variant(struct bz3_state *state, int stage, int variant);
-BZIP3_API int bz3_b200_get_variant(struct bz3_state *state, int stage);
-/* Decode-side kernels that the start-up self-test made the defaults (entropy decoders 8 / 9, the bulk LZP decoder) are
- * backed by the block checksum: a block that fails under them is decoded again with the round-1 kernels, whose verdict
- * the caller gets (so hostile input still yields the reference's error codes, src/libbz3.c:739-809); if the round-1
- * kernels decode it, the newer kernels are retired for the process.  Promoted encode-side kernels are cross-checked
- * against the round-1 kernels on the first block of every new size class (x2) and retired on a mismatch, the caller
- * getting the round-1 output.  Number of retirements (0 = never; anything else is a kernel bug worth reporting). */
-BZIP3_API int bz3_b200_demotions(void);
-
 /* The ".bz3" container of the reference's command line tool (src/main.c:157-482: "BZ3v1", s32 LE block size, then per
  * block s32 LE coded size, s32 LE original size, coded bytes) over file descriptors, with a deep block queue instead of
  * the reference's read-J / code-J / write-J batches (:352-478, J <= 64): a reader, `in_flight` workers (one state and
@@ -104,11 +90,6 @@ BZIP3_API int bz3_b200_decode_fd(int in_fd, int out_fd, int in_flight, uint64_t 
  * pass e.g. 64 x devices.  The plain entry points above are devices = 1 (one process per GPU, as bench.py runs). */
 BZIP3_API int bz3_b200_encode_fd2(int in_fd, int out_fd, int32_t block_size, int in_flight, int devices, uint64_t *bytes_in, uint64_t *bytes_out);
 BZIP3_API int bz3_b200_decode_fd2(int in_fd, int out_fd, int in_flight, int devices, uint64_t *bytes_in, uint64_t *bytes_out);
-/* the self-test behind the defaults, run in the calling process on `device` (used by the helper bz3_selftest, which the
- * library spawns so that a misbehaving candidate kernel can never take the caller's CUDA context down); returns 0 and
- * the kernels it would choose */
-BZIP3_API int bz3_b200_selftest(int device, int *cm_enc, int *cm_dec, int *lzp);
-
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ ROOT = refs.ROOT
 SO = os.path.join(ROOT, "tests", "_build", "libemucheck.so")
 SRCS = [os.path.join(ROOT, "tests", "native", f) for f in ("emu_check.cpp", "cta_emu.cpp")]
 DEPS = SRCS + [os.path.join(ROOT, "tests", "native", "cta_emu.h")] + [
-    os.path.join(ROOT, "bzip3_b200", "csrc", f) for f in ("common.cuh", "cm.cuh", "cm_dec.cuh", "cm_enc.cuh", "lzp.cuh", "lzp_parallel.cuh")]
+    os.path.join(ROOT, "bzip3_b200", "csrc", f) for f in ("common.cuh", "cm.cuh", "lzp.cuh", "lzp_parallel.cuh")]
 
 _lib = None
 
@@ -34,15 +34,11 @@ def emu():
         L = C.CDLL(SO)
         L.emu_set_schedule.argtypes = [C.c_int, C.c_ulonglong]
         L.emu_cm_encode.restype = C.c_int32
-        L.emu_cm_encode.argtypes = [C.c_int, refs.u8p, C.c_int32, refs.u8p]
+        L.emu_cm_encode.argtypes = [refs.u8p, C.c_int32, refs.u8p]
         L.emu_cm_decode.restype = C.c_int
-        L.emu_cm_decode.argtypes = [C.c_int, refs.u8p, C.c_int32, refs.u8p, C.c_int32]
+        L.emu_cm_decode.argtypes = [refs.u8p, C.c_int32, refs.u8p, C.c_int32]
         L.emu_lzp_encode.restype = C.c_int32
         L.emu_lzp_encode.argtypes = [refs.u8p, C.c_int32, refs.u8p, refs.i32p]
-        L.emu_lzp_encode_pf.restype = C.c_int32
-        L.emu_lzp_encode_pf.argtypes = [refs.u8p, C.c_int32, refs.u8p, refs.i32p]
-        L.emu_lzp_decode_bulk.restype = C.c_int32
-        L.emu_lzp_decode_bulk.argtypes = [refs.u8p, C.c_int32, refs.u8p, C.c_int32, refs.i32p]
         L.emu_lzp_decode.restype = C.c_int32
         L.emu_lzp_decode.argtypes = [refs.u8p, C.c_int32, refs.u8p, C.c_int32, refs.i32p]
         _lib = L
@@ -76,32 +72,23 @@ def cm_inputs():
 CM_CASES = cm_inputs()
 CM_IDS = [c[0] for c in CM_CASES]
 
-ENC_VARIANTS = [0, 1, 2, 4, 6, 10]
-DEC_VARIANTS = [0, 1, 3, 4, 5, 6, 7, 8, 9, 10]
 
-
-@pytest.mark.parametrize("variant", ENC_VARIANTS)
 @pytest.mark.parametrize("name,data", CM_CASES, ids=CM_IDS)
-def test_cm_encode_kernels(name, data, variant):
+def test_cm_encode_kernel(name, data):
     E, O = emu(), refs.oracle()
     n = len(data)
-    if variant in (1, 2) and n > 8000:
-        pytest.skip("cross-check kernel variants: small inputs only (suite time)")
     want = np.zeros(2 * n + 64, np.uint8)
     got = np.zeros(2 * n + 64, np.uint8)
     rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
-    rg = E.emu_cm_encode(variant, refs.ptr(data), n, refs.ptr(got))
+    rg = E.emu_cm_encode(refs.ptr(data), n, refs.ptr(got))
     assert rg == rw
     assert bytes(got[:rg]) == bytes(want[:rw])
 
 
-@pytest.mark.parametrize("variant", DEC_VARIANTS)
 @pytest.mark.parametrize("name,data", CM_CASES, ids=CM_IDS)
-def test_cm_decode_kernels(name, data, variant):
+def test_cm_decode_kernel(name, data):
     E, O = emu(), refs.oracle()
     n = len(data)
-    if variant in (1, 3, 5) and n > 8000:
-        pytest.skip("older kernel variants: small inputs only (suite time)")
     enc = np.zeros(2 * n + 64, np.uint8)
     r = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(enc))
     # the whole stream, a truncated stream (read_in() past the end adds -1) and an empty one
@@ -109,7 +96,7 @@ def test_cm_decode_kernels(name, data, variant):
         want = np.zeros(n + 8, np.uint8)
         got = np.zeros(n + 8, np.uint8)
         O.orc_cm_decode(refs.ptr(enc), insize, refs.ptr(want), n)
-        assert E.emu_cm_decode(variant, refs.ptr(enc), insize, refs.ptr(got), n) == 0
+        assert E.emu_cm_decode(refs.ptr(enc), insize, refs.ptr(got), n) == 0
         assert bytes(got[:n]) == bytes(want[:n]), (insize, r)
         if insize == r:
             assert bytes(got[:n]) == bytes(data)
@@ -125,14 +112,12 @@ def test_cm_kernels_other_schedules(schedule):
     rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
     E.emu_set_schedule(schedule, 4242)
     try:
-        for v in ENC_VARIANTS:
-            got = np.zeros(2 * n + 64, np.uint8)
-            assert E.emu_cm_encode(v, refs.ptr(data), n, refs.ptr(got)) == rw
-            assert bytes(got[:rw]) == bytes(want[:rw])
-        for v in DEC_VARIANTS:
-            back = np.zeros(n + 8, np.uint8)
-            E.emu_cm_decode(v, refs.ptr(want), rw, refs.ptr(back), n)
-            assert bytes(back[:n]) == bytes(data)
+        got = np.zeros(2 * n + 64, np.uint8)
+        assert E.emu_cm_encode(refs.ptr(data), n, refs.ptr(got)) == rw
+        assert bytes(got[:rw]) == bytes(want[:rw])
+        back = np.zeros(n + 8, np.uint8)
+        E.emu_cm_decode(refs.ptr(want), rw, refs.ptr(back), n)
+        assert bytes(back[:n]) == bytes(data)
     finally:
         E.emu_set_schedule(0, 1)
 
@@ -164,30 +149,19 @@ def test_lzp_warp_kernels(name, data):
     rw = O.orc_lzp_encode(refs.ptr(pad), n, refs.ptr(want), lp)
     rg = E.emu_lzp_encode(refs.ptr(pad), n, refs.ptr(got), lp)
     assert rg == rw
-    got2 = np.zeros(n + 64, np.uint8)
-    lut_after = lut.copy()
-    rg2 = E.emu_lzp_encode_pf(refs.ptr(pad), n, refs.ptr(got2), lp)   # several windows in flight
-    assert rg2 == rw
     if rw > 0:
         assert bytes(got[:rg]) == bytes(want[:rw])
-        assert bytes(got2[:rg2]) == bytes(want[:rw])
-        assert np.array_equal(lut, lut_after)   # same final table as the one-window kernel
         for cut in (rw, rw - 1, rw // 2, 4, 3):
             cap = refs.bound(n)
             dw = np.zeros(cap + 64, np.uint8)
             dg = np.zeros(cap + 64, np.uint8)
             sw = O.orc_lzp_decode(refs.ptr(want), cut, refs.ptr(dw), cap, lp)
+            lut_w = lut.copy()
             sg = E.emu_lzp_decode(refs.ptr(want), cut, refs.ptr(dg), cap, lp)
             assert sg == sw, (cut, sg, sw)
             if sw > 0:
                 assert bytes(dg[:sg]) == bytes(dw[:sw])
-            lut_w = lut.copy()
-            db = np.zeros(cap + 64, np.uint8)
-            sb = E.emu_lzp_decode_bulk(refs.ptr(want), cut, refs.ptr(db), cap, lp)   # bulk decoder
-            assert sb == sw, (cut, sb, sw)
-            if sw > 0:
-                assert bytes(db[:sb]) == bytes(dw[:sw])
-                assert np.array_equal(lut, lut_w)
+                assert np.array_equal(lut, lut_w)   # same final table as the reference's
         # output capacity smaller than the decoded size: the copy is clamped like the reference's
         for cap in (n // 2, 5):
             if cap < 4:
@@ -195,14 +169,14 @@ def test_lzp_warp_kernels(name, data):
             dw = np.zeros(n + 64, np.uint8)
             db = np.zeros(n + 64, np.uint8)
             sw = O.orc_lzp_decode(refs.ptr(want), rw, refs.ptr(dw), cap, lp)
-            sb = E.emu_lzp_decode_bulk(refs.ptr(want), rw, refs.ptr(db), cap, lp)
+            sb = E.emu_lzp_decode(refs.ptr(want), rw, refs.ptr(db), cap, lp)
             assert sb == sw, (cap, sb, sw)
             if sw > 0:
                 assert bytes(db[:sb]) == bytes(dw[:sw])
 
 
-def test_fuzz_all_variants_small_inputs():
-    """Random small inputs (several byte distributions) through every CM and LZP kernel variant."""
+def test_fuzz_small_inputs():
+    """Random small inputs (several byte distributions) through the CM and LZP kernels."""
     E, O = emu(), refs.oracle()
     rng = np.random.default_rng(20260923)
     lut = np.zeros(1 << 18, np.int32)
@@ -223,20 +197,18 @@ def test_fuzz_all_variants_small_inputs():
         n = len(data)
         want = np.zeros(2 * n + 64, np.uint8)
         rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
-        for v in ENC_VARIANTS:
-            got = np.zeros(2 * n + 64, np.uint8)
-            assert E.emu_cm_encode(v, refs.ptr(data), n, refs.ptr(got)) == rw, (it, v)
-            assert bytes(got[:rw]) == bytes(want[:rw]), (it, v)
+        got = np.zeros(2 * n + 64, np.uint8)
+        assert E.emu_cm_encode(refs.ptr(data), n, refs.ptr(got)) == rw, it
+        assert bytes(got[:rw]) == bytes(want[:rw]), it
         cut = int(rng.integers(0, rw + 1))
         dw = np.zeros(n + 8, np.uint8)
         O.orc_cm_decode(refs.ptr(want), cut, refs.ptr(dw), n)
-        for v in DEC_VARIANTS:
-            back = np.zeros(n + 8, np.uint8)
-            E.emu_cm_decode(v, refs.ptr(want), rw, refs.ptr(back), n)
-            assert bytes(back[:n]) == bytes(data), (it, v)
-            back = np.zeros(n + 8, np.uint8)
-            E.emu_cm_decode(v, refs.ptr(want), cut, refs.ptr(back), n)
-            assert bytes(back[:n]) == bytes(dw[:n]), (it, v, cut)
+        back = np.zeros(n + 8, np.uint8)
+        E.emu_cm_decode(refs.ptr(want), rw, refs.ptr(back), n)
+        assert bytes(back[:n]) == bytes(data), it
+        back = np.zeros(n + 8, np.uint8)
+        E.emu_cm_decode(refs.ptr(want), cut, refs.ptr(back), n)
+        assert bytes(back[:n]) == bytes(dw[:n]), (it, cut)
         # LZP on a longer, matchy input built from the same bytes
         long = np.ascontiguousarray(np.tile(data, 1 + 1200 // n)[:1200 + n])
         m = len(long)
@@ -244,7 +216,7 @@ def test_fuzz_all_variants_small_inputs():
         pad[:m] = long
         lw = np.zeros(m + 64, np.uint8)
         r0 = O.orc_lzp_encode(refs.ptr(pad), m, refs.ptr(lw), lp)
-        for fn in (E.emu_lzp_encode, E.emu_lzp_encode_pf):
+        for fn in (E.emu_lzp_encode,):
             lg = np.zeros(m + 64, np.uint8)
             assert fn(refs.ptr(pad), m, refs.ptr(lg), lp) == r0, it
             if r0 > 0:
@@ -254,7 +226,7 @@ def test_fuzz_all_variants_small_inputs():
             for cutl in (r0, int(rng.integers(0, r0 + 1))):
                 d0 = np.zeros(cap + 64, np.uint8)
                 s0 = O.orc_lzp_decode(refs.ptr(lw), cutl, refs.ptr(d0), cap, lp)
-                for fn in (E.emu_lzp_decode, E.emu_lzp_decode_bulk):
+                for fn in (E.emu_lzp_decode,):
                     d1 = np.zeros(cap + 64, np.uint8)
                     assert fn(refs.ptr(lw), cutl, refs.ptr(d1), cap, lp) == s0, (it, cutl)
                     if s0 > 0:

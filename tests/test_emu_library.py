@@ -72,28 +72,6 @@ def test_block_roundtrip_vs_oracle(st, name, data):
         assert st.last_error == 0
 
 
-@pytest.mark.parametrize("enc_v,dec_v,lzp_v", [(4, 4, 3), (6, 9, 2), (6, 5, 2), (0, 8, 2)])
-def test_block_roundtrip_with_other_kernels(st, enc_v, dec_v, lzp_v):
-    """The opt-in entropy / LZP kernels selected through the block API give the same bytes."""
-    L = st.L
-    datas = [synth.zipf_text(1500, seed=3).tobytes(), synth.log_stream(2000, seed=4).tobytes(),
-             bytes(np.repeat(np.arange(40, dtype=np.uint8), 40))]
-    L.bz3_b200_set_variant(st.handle, 5 + 100, enc_v)
-    L.bz3_b200_set_variant(st.handle, 5 + 200, dec_v)
-    L.bz3_b200_set_variant(st.handle, 3, lzp_v)
-    try:
-        assert L.bz3_b200_get_variant(st.handle, 5 + 100) == enc_v and L.bz3_b200_get_variant(st.handle, 5 + 200) == dec_v
-        for data in datas:
-            enc_o, r_o, _ = refs.oracle_encode_block(data, BS)
-            enc_g, r_g = st.encode_block(data)
-            assert r_g == r_o and enc_g == enc_o
-            dec, r = st.decode_block(enc_o, len(data))
-            assert r == len(data) and dec == data
-    finally:
-        L.bz3_b200_set_variant(st.handle, 5, 0)
-        L.bz3_b200_set_variant(st.handle, 3, 0)
-
-
 def test_block_too_big_and_raw_paths(st):
     enc, r = st.encode_block(bytes(BS + 1))
     assert r == -1 and st.last_error == bzip3_b200.BZ3_ERR_DATA_TOO_BIG
@@ -168,37 +146,6 @@ def test_frame_api_and_helpers(emulib):
     assert not L.bz3_new(1000) and not L.bz3_new((511 << 20) + 1)   # block size out of range
 
 
-def test_default_kernels_come_from_the_self_test(emulib):
-    """bz3_new runs the on-device self-test once per process (kernel_autoselect in bz3_api.cu): the newer kernels
-    become the defaults only if they reproduce the proven kernels' bytes and are faster.  Here (emulator, where they
-    are slower) the proven ones must stay; with BZ3_B200_AUTOSELECT=force a fresh process must select the newer
-    ones -- which proves that every comparison of the self-test passes -- and still code blocks bit-exactly."""
-    import subprocess
-    import sys
-    with bzip3_b200.Bz3State(BS) as s:
-        got = (emulib.bz3_b200_get_variant(s.handle, 105), emulib.bz3_b200_get_variant(s.handle, 205),
-               emulib.bz3_b200_get_variant(s.handle, 3))
-    assert got[0] in (0, 6) and got[1] in (0, 8, 9) and got[2] in (3, 2)
-    script = (
-        "import os, sys\n"
-        "sys.path.insert(0, %r)\n"
-        "import bzip3_b200\n"
-        "from bzip3_b200 import synth\n"
-        "from tests import refs\n"
-        "data = synth.zipf_text(1500, seed=2).tobytes()\n"
-        "with bzip3_b200.Bz3State(%d) as s:\n"
-        "    L = s.L\n"
-        "    print('CHOICE', L.bz3_b200_get_variant(s.handle, 105), L.bz3_b200_get_variant(s.handle, 205), L.bz3_b200_get_variant(s.handle, 3))\n"
-        "    enc, r = s.encode_block(data)\n"
-        "    want = refs.oracle_encode_block(data, %d)\n"
-        "    dec, r2 = s.decode_block(enc, len(data))\n"
-        "    print('EXACT', r == want[1] and enc == want[0] and dec == data)\n" % (ROOT, BS, BS))
-    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="force")
-    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
-    assert "CHOICE 6 8 2" in out.stdout or "CHOICE 6 9 2" in out.stdout, out.stdout + out.stderr
-    assert "EXACT True" in out.stdout, out.stdout + out.stderr
-
-
 def test_stage_workspaces_are_shared_by_the_states_of_a_device(emulib, st):
     """The 48 B/B scratch of mRLE / suffix sort / inverse BWT is a per-device pool leased per stage call (ArenaPool in
     bz3_api.cu), not a per-state allocation: what a state owns is three block buffers and the LZP table."""
@@ -257,7 +204,7 @@ def test_one_workspace_serves_a_batch_of_blocks(emulib):
         "with bzip3_b200.Bz3State(bs) as s:\n"
         "    ok = ok and s.encode_block(datas[0])[0] == refs.oracle_encode_block(datas[0], bs)[0]\n"
         "print('EXACT', ok)\n" % (ROOT, BS))
-    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_ARENAS="1", BZ3_B200_AUTOSELECT="0")
+    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_ARENAS="1")
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
     assert "WORKSPACE 1" in out.stdout, out.stdout + out.stderr
     assert "EXACT True" in out.stdout, out.stdout + out.stderr
@@ -292,127 +239,8 @@ def test_out_of_device_memory_is_reported_by_bz3_new_and_spares_the_live_states(
         "    ok = ok and r == want[1] and enc == want[0] and dec == data\n"
         "print('EXACT', ok)\n" % (ROOT, BS))
     cap = 48 * 3 * BS   # enough for the workspace of a BS state (and for block buffers), not for an 8 * BS state
-    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="0", BZ_EMU_MALLOC_MAX=str(cap))
+    env = dict(os.environ, BZ3_B200_LIB=SO, BZ_EMU_MALLOC_MAX=str(cap))
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
     assert "LONE True True" in out.stdout, out.stdout + out.stderr   # a lone state gets one workspace, the second state the second
     assert "BIG None" in out.stdout, out.stdout + out.stderr
     assert "SAME True" in out.stdout and "EXACT True" in out.stdout, out.stdout + out.stderr
-
-
-def test_a_promoted_decoder_that_errs_is_caught_by_the_block_checksum(emulib):
-    """Kernels promoted by the self-test are backed by the block checksum (decode_checked in bz3_api.cu): a block that
-    fails under them is decoded again with the round-1 kernels.  A really corrupt block keeps the promoted kernels and
-    gets the oracle's error; a good block that a (here: sabotaged) promoted decoder gets wrong still decodes, and the
-    promoted kernels are retired for the process."""
-    import subprocess
-    import sys
-    script = (
-        "import sys\n"
-        "sys.path.insert(0, %r)\n"
-        "import bzip3_b200\n"
-        "from bzip3_b200 import synth\n"
-        "from tests import refs\n"
-        "bs = %d\n"
-        "good = synth.zipf_text(1500, seed=2).tobytes()\n"
-        "other = synth.zipf_text(1400, seed=3).tobytes()\n"
-        "with bzip3_b200.Bz3State(bs) as s, bzip3_b200.Bz3State(bs) as t:\n"
-        "    L = s.L\n"
-        "    print('START', L.bz3_b200_get_variant(s.handle, 205) in (8, 9), L.bz3_b200_demotions())\n"
-        "    enc, r = s.encode_block(other)\n"
-        "    bad = bytearray(enc); bad[len(bad) // 2] ^= 0x55; bad = bytes(bad)\n"
-        "    want = refs.oracle_decode_block(bad, len(other), bs, err_init=55)\n"
-        "    dec, r2 = s.decode_block(bad, len(other))\n"
-        "    print('CORRUPT', r2 == want[1] and s.last_error == want[2], L.bz3_b200_demotions(), L.bz3_b200_get_variant(s.handle, 205) in (8, 9))\n"
-        "    dec, r2 = s.decode_block(enc, len(other))\n"
-        "    print('FINE', dec == other, L.bz3_b200_demotions())\n"
-        "    enc, r = s.encode_block(good)            # 1500 bytes reach the entropy stage: the sabotaged size\n"
-        "    dec, r2 = s.decode_block(enc, len(good))\n"
-        "    print('RESCUED', dec == good and r2 == len(good) and s.last_error == 0, L.bz3_b200_demotions(), L.bz3_b200_get_variant(s.handle, 205))\n"
-        "    dec, r2 = t.decode_block(enc, len(good))  # a state created before the demotion follows at its next block\n"
-        "    print('OTHER', dec == good, L.bz3_b200_get_variant(t.handle, 205), L.bz3_b200_demotions())\n"
-        "with bzip3_b200.Bz3State(bs) as u:\n"
-        "    print('NEW', u.L.bz3_b200_get_variant(u.handle, 205), u.L.bz3_b200_get_variant(u.handle, 3))\n"
-        "    u.L.bz3_b200_set_variant(u.handle, 205, 9)   # the user's own choice gets no second opinion\n"
-        "    dec, r2 = u.decode_block(enc, len(good))\n"
-        "    print('PINNED', r2, u.last_error, u.L.bz3_b200_demotions())\n" % (ROOT, BS))
-    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="force", BZ_EMU_SABOTAGE_DEC_N="1500")
-    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
-    text = out.stdout + out.stderr
-    assert "START True 0" in text, text
-    assert "CORRUPT True 0 True" in text, text
-    assert "FINE True 0" in text, text
-    assert "RESCUED True 1 0" in text, text
-    assert "OTHER True 0 1" in text, text
-    assert "NEW 0 3" in text, text
-    assert "PINNED -1 %d 1" % bzip3_b200.BZ3_ERR_CRC in text, text
-    assert "retired for this process" in text, text
-
-
-def test_a_promoted_encoder_is_cross_checked_once_per_size_class(emulib):
-    """Encode side of the safety net (Probation in bz3_api.cu): the first block of every size class (more than twice the
-    largest size checked so far) is also coded by the round-1 kernel.  A (here: sabotaged) promoted encoder that gets a
-    byte wrong on such a block is caught before the caller sees the block: the round-1 stream is returned, every promoted
-    kernel of the process is retired."""
-    import subprocess
-    import sys
-    script = (
-        "import sys\n"
-        "sys.path.insert(0, %r)\n"
-        "import bzip3_b200\n"
-        "from bzip3_b200 import synth\n"
-        "from tests import refs\n"
-        "bs = %d\n"
-        "def exact(s, data):\n"
-        "    enc, r = s.encode_block(data)\n"
-        "    want = refs.oracle_encode_block(data, bs)\n"
-        "    return r == want[1] and enc == want[0]\n"
-        "with bzip3_b200.Bz3State(bs) as s:\n"
-        "    L = s.L\n"
-        "    print('START', L.bz3_b200_get_variant(s.handle, 105), L.bz3_b200_demotions())\n"
-        "    print('SMALL', exact(s, synth.zipf_text(700, seed=1).tobytes()), L.bz3_b200_demotions(), L.bz3_b200_get_variant(s.handle, 105))\n"
-        "    print('SAMECLASS', exact(s, synth.zipf_text(1300, seed=2).tobytes()), L.bz3_b200_demotions())\n"
-        "    print('CAUGHT', exact(s, synth.zipf_text(1500, seed=3).tobytes()), L.bz3_b200_demotions(), L.bz3_b200_get_variant(s.handle, 105))\n"
-        "    print('AFTER', exact(s, synth.zipf_text(1500, seed=4).tobytes()), L.bz3_b200_demotions())\n"
-        "with bzip3_b200.Bz3State(bs) as t:\n"
-        "    print('NEW', t.L.bz3_b200_get_variant(t.handle, 105), t.L.bz3_b200_get_variant(t.handle, 205), t.L.bz3_b200_get_variant(t.handle, 3))\n" % (ROOT, BS))
-    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="force", BZ3_B200_PROBATION_FROM="0", BZ_EMU_SABOTAGE_ENC_N="1500")
-    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
-    text = out.stdout + out.stderr
-    assert "START 6 0" in text, text
-    assert "SMALL True 0 6" in text, text          # first block: checked, agrees
-    assert "SAMECLASS True 0" in text, text        # 1300 <= 2 * 700: not checked again
-    assert "CAUGHT True 1 0" in text, text         # 1500 > 2 * 700: checked, the sabotaged stream never reaches the caller
-    assert "AFTER True 1" in text, text
-    assert "NEW 0 0 3" in text, text
-    assert "disagrees with the round-1 kernel" in text, text
-    # without the net the same block comes out wrong -- the hook really bites
-    env2 = dict(env, BZ3_B200_PROBATION_FROM="100000")
-    out = subprocess.run([sys.executable, "-c", script], env=env2, capture_output=True, text=True, timeout=900)
-    assert "CAUGHT False 0 6" in out.stdout, out.stdout + out.stderr
-
-
-def test_a_promoted_lzp_encoder_is_cross_checked_too(emulib):
-    import subprocess
-    import sys
-    script = (
-        "import sys\n"
-        "sys.path.insert(0, %r)\n"
-        "import bzip3_b200\n"
-        "from bzip3_b200 import synth\n"
-        "from tests import refs\n"
-        "bs = %d\n"
-        "line = synth.log_stream(200, seed=3).tobytes()\n"
-        "data = (line * 10)[:1500]\n"
-        "with bzip3_b200.Bz3State(bs) as s:\n"
-        "    L = s.L\n"
-        "    enc, r = s.encode_block(data)\n"
-        "    want = refs.oracle_encode_block(data, bs)\n"
-        "    print('MODEL', want[0][8] & 2, 'EXACT', r == want[1] and enc == want[0], L.bz3_b200_demotions(), L.bz3_b200_get_variant(s.handle, 3))\n" % (ROOT, BS))
-    env = dict(os.environ, BZ3_B200_LIB=SO, BZ3_B200_AUTOSELECT="force", BZ3_B200_PROBATION_FROM="0", BZ_EMU_SABOTAGE_LZP_N="1500")
-    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
-    text = out.stdout + out.stderr
-    assert "MODEL 2 EXACT True 1 3" in text, text       # LZP was in use on this block; caught, round-1 output returned
-    assert "promoted LZP encoder disagrees" in text, text
-    out = subprocess.run([sys.executable, "-c", script], env=dict(env, BZ3_B200_PROBATION_FROM="100000"), capture_output=True,
-                         text=True, timeout=900)
-    assert "EXACT False 0 2" in out.stdout, out.stdout + out.stderr   # without the net the hook bites

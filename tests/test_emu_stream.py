@@ -211,7 +211,7 @@ def test_command_line_tool(L, tmp_path):
     cli = os.path.join(refs.ROOT, "bzip3_b200", "bz3b200")
     if not (os.path.exists(cli) and os.access(cli, os.X_OK)):
         pytest.skip("bzip3_b200/bz3b200 not built")
-    env = dict(os.environ, BZ3_B200_LIB=build_emulated_library(), BZ3_B200_AUTOSELECT="0")
+    env = dict(os.environ, BZ3_B200_LIB=build_emulated_library())
     data = synth.zipf_text(1800, seed=12).tobytes()
     src, packed, back = tmp_path / "a.txt", tmp_path / "a.bz3", tmp_path / "a.out"
     src.write_bytes(data)

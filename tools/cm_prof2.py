@@ -1,6 +1,6 @@
 """clock64 phase breakdown of the entropy-stage kernels (needs tools/variants/lib_cmprof.so = the library built
 with -DBZ_CM_PROFILE; see tools/README in DESIGN.md section 6).  Prints cycles per input byte for every
-phase of: encoder v0 / v4, decoder v0 (tree), v4 (lane-parallel chain warp), v5 (all paths v2).
+phase of the encoder (two model stages, coder lane) and of the decoder's chain warp.
 ctypes + numpy only."""
 import ctypes as C
 import json
@@ -38,34 +38,15 @@ def main():
             L.bz3_b200_stage_bwt(st.handle, data.ctypes.data_as(u8p), n, bwt.ctypes.data_as(u8p))
             enc = np.zeros(2 * n + 64, np.uint8)
             rec = {}
-            for v in [int(x) for x in os.environ.get('BZ3_PROF_ENC', '0,4,6').split(',')]:
-                L.bz3_b200_set_variant(st.handle, CM + 100, v)
-                r = L.bz3_b200_stage_cm_encode(st.handle, bwt.ctypes.data_as(u8p), n, enc.ctypes.data_as(u8p))
-                p = prof()
-                rec["enc_v%d" % v] = {"stage1_busy": p[13] / n, "stage2_busy": p[14] / n, "coder_busy": p[15] / n,
-                                      "exact_tier_cycles": p[32] / n, "exact_tier_bytes_frac": p[33] / n}
-            for v in [int(x) for x in os.environ.get('BZ3_PROF_DEC', '0,4,5,6,7,8,9,10').split(',')]:
-                L.bz3_b200_set_variant(st.handle, CM + 200, v)
-                back = np.zeros(n + 8, np.uint8)
-                L.bz3_b200_stage_cm_decode(st.handle, enc.ctypes.data_as(u8p), r, back.ctypes.data_as(u8p), n)
-                assert bytes(back[:n]) == bytes(bwt[:n]), (name, v)
-                p = prof()
-                if v == 0:
-                    rec["dec_v0_chain"] = dict(zip(("wait_ptab", "fast_tier", "exact_tier", "publish_wait_byte", "redo_frac"),
-                                                   [x / n for x in p[8:13]]))
-                elif v == 10:
-                    rec["dec_v10_walker"] = dict(zip(("first_table", "walk", "publish_wait_spec", "wait_real", "miss_frac"),
-                                                     [x / n for x in p[8:13]]))
-                elif v == 4:
-                    rec["dec_v4_chain"] = dict(zip(("wait_ptab", "round1_fast", "round1_exact", "round2_fast", "round2_exact",
-                                                    "publish_wait_byte", "fb1_frac", "fb2_frac"), [x / n for x in p[16:24]]))
-                elif v == 5:
-                    rec["dec_v5_thread0"] = dict(zip(("predict", "wait_S1", "walk", "wait_S2", "fallback", "learn", "fallback_frac"),
-                                                     [x / n for x in p[24:31]]))
-                else:
-                    rec["dec_v%d_walker0" % v] = dict(zip(("wait_B1", "walk", "wait_B2", "slow_path", "tail", "slow_frac",
-                                                           "serial_frac"), [x / n for x in p[36:43]]))
-            L.bz3_b200_set_variant(st.handle, CM, 0)
+            r = L.bz3_b200_stage_cm_encode(st.handle, bwt.ctypes.data_as(u8p), n, enc.ctypes.data_as(u8p))
+            p = prof()
+            rec["encoder"] = {"stage1_busy": p[13] / n, "stage2_busy": p[14] / n, "coder_busy": p[15] / n}
+            back = np.zeros(n + 8, np.uint8)
+            L.bz3_b200_stage_cm_decode(st.handle, enc.ctypes.data_as(u8p), r, back.ctypes.data_as(u8p), n)
+            assert bytes(back[:n]) == bytes(bwt[:n]), name
+            p = prof()
+            rec["decoder_chain_warp"] = dict(zip(("wait_ptab", "fast_tier", "exact_tier", "publish_wait_byte", "redo_frac"),
+                                                 [x / n for x in p[8:13]]))
             out[name] = rec
             print(name)
             for k, d in rec.items():

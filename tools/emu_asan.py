@@ -31,23 +31,19 @@ def main():
     bs = 65 * 1024 + 1024
     cases = [(n, bytes(d[:1200])) for n, d in synth.edge_cases()]
     with bzip3_b200.Bz3State(bs) as s:
-        for enc_v, dec_v, lzp_v in ((0, 0, 0), (6, 9, 2), (4, 4, 0), (6, 5, 2), (0, 8, 2), (6, 7, 0), (6, 6, 2)):
-            s.L.bz3_b200_set_variant(s.handle, 105, enc_v)
-            s.L.bz3_b200_set_variant(s.handle, 205, dec_v)
-            s.L.bz3_b200_set_variant(s.handle, 3, lzp_v)
+        if True:
             for name, data in cases:
                 enc, r = s.encode_block(data)
                 want = refs.oracle_encode_block(data, bs)
-                assert r == want[1] and enc == want[0], (enc_v, dec_v, lzp_v, name)
+                assert r == want[1] and enc == want[0], name
                 dec, r2 = s.decode_block(enc, len(data))
-                assert dec == data, (enc_v, dec_v, lzp_v, name)
+                assert dec == data, name
                 if len(enc) > 40:   # a damaged block must not make any kernel read or write out of bounds either
                     bad = bytearray(enc)
                     bad[len(bad) // 2] ^= 0x10
                     s.decode_block(bytes(bad), len(data))
                     s.decode_block(enc[: len(enc) // 2], len(data))
-            print("encoder %d / decoder %d / LZP %d: %d cases round-tripped, no AddressSanitizer report" % (
-                enc_v, dec_v, lzp_v, len(cases)), flush=True)
+            print("%d cases round-tripped, damaged and truncated blocks decoded, no AddressSanitizer report" % len(cases), flush=True)
     # the file container front end (csrc/stream.h): reader, workers and writer threads on a file of three blocks, whole
     # and cut short inside a block
     import ctypes as C

@@ -79,18 +79,18 @@ def child(kind, variant):
     elif kind in ("enc", "dec"):
         L = C.CDLL(KSO)
         L.emu_cm_encode.restype = C.c_int32
-        L.emu_cm_encode.argtypes = [C.c_int, u8p, C.c_int32, u8p]
-        L.emu_cm_decode.argtypes = [C.c_int, u8p, C.c_int32, u8p, C.c_int32]
+        L.emu_cm_encode.argtypes = [u8p, C.c_int32, u8p]
+        L.emu_cm_decode.argtypes = [u8p, C.c_int32, u8p, C.c_int32]
         data = bwt(synth.zipf_text(N, seed=7))
         n = len(data)
         want = np.zeros(2 * n + 64, np.uint8)
         rw = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(want))
         if kind == "enc":
             got = np.zeros(2 * n + 64, np.uint8)
-            ok = L.emu_cm_encode(variant, refs.ptr(data), n, refs.ptr(got)) == rw and bytes(got[:rw]) == bytes(want[:rw])
+            ok = L.emu_cm_encode(refs.ptr(data), n, refs.ptr(got)) == rw and bytes(got[:rw]) == bytes(want[:rw])
         else:
             back = np.zeros(n + 8, np.uint8)
-            L.emu_cm_decode(variant, refs.ptr(want), rw, refs.ptr(back), n)
+            L.emu_cm_decode(refs.ptr(want), rw, refs.ptr(back), n)
             ok = bytes(back[:n]) == bytes(data)
     elif kind == "lzp":
         L = C.CDLL(KSO)
@@ -102,8 +102,7 @@ def child(kind, variant):
         lp = lut.ctypes.data_as(refs.i32p)
         lw = np.zeros(m + 64, np.uint8)
         r0 = O.orc_lzp_encode(refs.ptr(pad), m, refs.ptr(lw), lp)
-        enc = L.emu_lzp_encode_pf if variant == 2 else L.emu_lzp_encode
-        dec = L.emu_lzp_decode_bulk if variant == 2 else L.emu_lzp_decode
+        enc, dec = L.emu_lzp_encode, L.emu_lzp_decode
         for f in (enc, dec):
             f.restype = C.c_int32
         enc.argtypes = [u8p, C.c_int32, u8p, refs.i32p]
@@ -155,9 +154,9 @@ def main():
     bad = 0
     for kind, v in jobs:
         if kind == "lib":
-            env = dict(env, BZ3_B200_LIB=LSO, BZ3_B200_ARENAS=str(v), BZ3_B200_AUTOSELECT="0")
+            env = dict(env, BZ3_B200_LIB=LSO, BZ3_B200_ARENAS=str(v))
         if kind == "stream":
-            env = dict(env, BZ3_B200_LIB=LSO, BZ3_B200_AUTOSELECT="0")
+            env = dict(env, BZ3_B200_LIB=LSO)
         out = subprocess.run([sys.executable, os.path.abspath(__file__), kind, str(v)], env=env, capture_output=True, text=True)
         text = out.stdout + out.stderr
         result = "bit-exact" if "RESULT bit-exact" in text else "NO RESULT / WRONG OUTPUT"

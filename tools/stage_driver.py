@@ -23,8 +23,6 @@ def main():
     u8p = C.POINTER(C.c_uint8)
     with bzip3_b200.Bz3State(bs) as s:
         import os
-        L.bz3_b200_set_variant(s.handle, 5, int(os.environ.get('BZ3_VARIANT_CM', '0')))
-        L.bz3_b200_set_variant(s.handle, 3, int(os.environ.get('BZ3_VARIANT_LZP', '0')))
         out = np.zeros(bzip3_b200.bound(n) + 64, np.uint8)
         back = np.zeros(bzip3_b200.bound(n) + 64, np.uint8)
         pi, po, pb = (a.ctypes.data_as(u8p) for a in (data, out, back))
