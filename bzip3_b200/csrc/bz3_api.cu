@@ -24,6 +24,7 @@
 #include "mrle.cuh"
 #include "lzp.cuh"
 #include "lzp_parallel.cuh"
+#include "lzp_scan.cuh"
 #include "sufsort.cuh"
 #include "unbwt.cuh"
 #include "cm.cuh"
@@ -238,11 +239,16 @@ size_t sufsort_arena_bytes(size_t n) {
     return align_up(4 * n) + align_up(4 * (n + 1)) + 2 * align_up(8 * n) + 6 * align_up(4 * n) +
            align_up(4 * sufsort_temp_elems((u32)n)) + 16 * kAlign;
 }
+size_t lzp_arena_bytes(size_t n) {
+    return 4 * align_up(4 * n) + align_up(4 * (n + 8)) + align_up(n + 8) + align_up(4 * ((n + 31) / 32 + 1)) +
+           align_up(4 * rs_temp_elems<u32>((u32)n)) + 16 * kAlign;
+}
 size_t other_arena_bytes(size_t n) {
     size_t mr = align_up(4 * (n + 2)) + align_up(12 * scan_temp_elems((u32)n)) + align_up(n) + 8 * kAlign;
     size_t ub = align_up(4 * (n + 2)) + 5 * align_up(4 * ((n >> 5) + 8)) + align_up(4 * rs_temp_elems<u8>((u32)n)) +
                 align_up(65536 * 4) + 8 * kAlign;
-    return mr > ub ? mr : ub;
+    const size_t lz = lzp_arena_bytes(n);
+    return std::max(lz, mr > ub ? mr : ub);
 }
 
 bool carve_sufsort(bz3_state* s, u32 n, SufsortBuffers& B) {   // inside an ArenaLease
@@ -333,13 +339,24 @@ cudaError_t run_rle_decode(bz3_state* s, const u8* d_in, u32 maxin, u8* d_out, u
 }
 
 cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* result) {
-    if (n < kLzpMinMatch + 32) { *result = -1; return cudaSuccess; }
-    BZ_CUDA_TRY(cudaMemsetAsync(s->d_lut, 0, sizeof(s32) * kLzpSlots, s->stream));
-    BZ_LAUNCH(1, 32, 0, s->stream, lzp_encode_warp_kernel)(d_in, n, d_out, s->d_lut, reinterpret_cast<s32*>(s->d_scal + 8));
-    BZ_NOTE_LAUNCH();
-    BZ_CUDA_TRY(cudaGetLastError());
+    if (n < kLzpMinMatch + 32) { *result = -1; return cudaSuccess; }   // src/libbz3.c:244
+    ArenaLease lease(s, BZ3_STAGE_LZP);
+    if (!lease.ok()) return cudaErrorMemoryAllocation;
+    Arena& A = s->arena;
+    A.reset();
+    LzpScanBuffers B;
+    const u32 m = (u32)n - 4u;
+    for (int i = 0; i < 2; i++) B.key[i] = A.take<u32>(m);
+    for (int i = 0; i < 2; i++) B.idx[i] = A.take<u32>(m);
+    B.P = A.take<u32>((size_t)n + 8);
+    B.code = A.take<u8>((size_t)n + 8);
+    B.skipbits = A.take<u32>((size_t)(n + 31) / 32 + 1);
+    B.temp = A.take<u32>(rs_temp_elems<u32>(m));
+    if (!B.temp) return cudaErrorMemoryAllocation;
+    s32* d_res = reinterpret_cast<s32*>(s->d_scal + 8);
+    BZ_CUDA_TRY(lzp_scan_encode(s->stream, d_in, n, d_out, B, d_res));
     BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));   // see run_cm_encode: nothing waits in a queue behind a long kernel
-    BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, s->d_scal + 8, 4, cudaMemcpyDeviceToHost, s->stream));
+    BZ_CUDA_TRY(cudaMemcpyAsync(s->h_scal + 8, d_res, 4, cudaMemcpyDeviceToHost, s->stream));
     BZ_CUDA_TRY(cudaStreamSynchronize(s->stream));
     *result = (s32)s->h_scal[8];
     return cudaSuccess;

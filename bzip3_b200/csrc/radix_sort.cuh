@@ -3,14 +3,18 @@
 // This is the engine behind the suffix sorter (64-bit keys = (rank[i], rank[i+h]), 32-bit values =
 // suffix index) and the psi construction of the inverse BWT (8-bit keys, generated values).
 //
-// One pass = three launches and no inter-CTA spinning:
-//   tile_hist   : every CTA counts the digits of its tile        -> hist[digit][tile]   (reads keys)
-//   device_scan : exclusive scan of hist in digit-major order    -> global base of each (digit, tile)
-//   scatter     : every CTA re-reads its tile, ranks the records stably inside the tile
-//                 (warp match + per-warp counters), stages the tile in shared memory in sorted order
-//                 and writes each digit's records as one contiguous, coalesced run.
-// Algorithmic HBM bytes per pass over m records: sizeof(K)*m (hist) + (sizeof(K)+4)*m read
-// + (sizeof(K)+4)*m written; for the 64-bit-key sort that is 32 B per record per pass.
+// One sort = one histogram launch + ONE launch per pass ("one sweep"):
+//   hist_all    : the digit histograms of EVERY pass in one read of the keys (they do not depend on the order of the
+//                 records), then their exclusive scans over the digits -> gbase[pass][digit]
+//   pass        : every CTA takes the next tile (atomic ticket), brings it into shared memory with one bulk async copy
+//                 per array (TMA: cp.async.bulk + mbarrier), ranks the records stably inside the tile (warp match +
+//                 per-warp counters), publishes its per-digit counts and finds the counts of the tiles before it by
+//                 decoupled look-back (descriptor word = 2 flag bits + 30-bit count: "tile total" first, "inclusive
+//                 prefix" once known), stages the tile in shared memory in sorted order and writes each digit's records
+//                 as one contiguous, coalesced run.
+// Algorithmic HBM bytes per pass over m records: (sizeof(K)+4)*m read + (sizeof(K)+4)*m written -- 24 B per record per
+// pass for the 64-bit-key sort of the suffix sorter -- plus sizeof(K)*m once per sort for the histograms and 1 KiB of
+// descriptors per tile of 3072 records.
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -55,63 +59,173 @@ struct ValIdentity {
     BZ_D u32 operator()(u32 i) const { return i; }
 };
 
+constexpr u32 kRsFlagAgg = 1u << 30;   // descriptor holds the tile's own count of the digit
+constexpr u32 kRsFlagInc = 2u << 30;   // descriptor holds the inclusive prefix over tiles 0..t
+constexpr u32 kRsValMask = (1u << 30) - 1u;   // n < 2^30 (blocks are at most 511 MiB + 2 %)
+constexpr int kRsMaxPasses = 8;
+
+// digit histograms of all passes in one read of the keys: ghist[pass][256] (zeroed by the caller)
 template <typename K>
-__global__ void __launch_bounds__(kRsThreads)
-rs_tile_hist_kernel(const K* __restrict__ keys, u32 n, int shift, u32 mask, u32* __restrict__ hist, u32 ntiles) {
-    constexpr int ITEMS = RsCfg<K>::kItems;
-    constexpr u32 TILE = kRsThreads * ITEMS;
+__global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const K* __restrict__ keys, u32 n, int nbits, u32* __restrict__ ghist) {
+    constexpr int ITEMS = 8;
     __shared__ u32 cnt[kRsWarps][256];
-    for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) (&cnt[0][0])[i] = 0;
-    __syncthreads();
     const u32 w = warp_id(), l = lane_id();
-    const u32 base = blockIdx.x * TILE + w * (32 * ITEMS);
+    const int npass = (nbits + 7) / 8;
+    for (u32 tile = blockIdx.x; (u64)tile * (kRsThreads * ITEMS) < n; tile += gridDim.x) {
+        const u32 base = tile * (kRsThreads * ITEMS) + w * (32 * ITEMS);
+        K key[ITEMS];
 #pragma unroll
-    for (int it = 0; it < ITEMS; it++) {
-        u32 i = base + it * 32 + l;
-        if (i < n) atomicAdd(&cnt[w][rs_digit(keys[i], shift, mask)], 1u);
-    }
-    __syncthreads();
-    {
-        u32 d = threadIdx.x, s = 0;
+        for (int it = 0; it < ITEMS; it++) {
+            const u32 i = base + it * 32 + l;
+            key[it] = (i < n) ? keys[i] : (K)0;
+        }
+        for (int p = 0; p < npass; p++) {
+            const int shift = 8 * p;
+            const u32 mask = (nbits - shift < 8) ? ((1u << (nbits - shift)) - 1u) : 255u;
+            for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) (&cnt[0][0])[i] = 0;
+            __syncthreads();
 #pragma unroll
-        for (int k = 0; k < kRsWarps; k++) s += cnt[k][d];
-        hist[d * ntiles + blockIdx.x] = s;
+            for (int it = 0; it < ITEMS; it++) {
+                const u32 i = base + it * 32 + l;
+                if (i < n) atomicAdd(&cnt[w][rs_digit(key[it], shift, mask)], 1u);
+            }
+            __syncthreads();
+            {
+                const u32 d = threadIdx.x;
+                u32 sum = 0;
+#pragma unroll
+                for (int k = 0; k < kRsWarps; k++) sum += cnt[k][d];
+                if (sum) atomicAdd(&ghist[p * 256 + d], sum);
+            }
+            __syncthreads();
+        }
     }
 }
 
-// KOUT: write keys;  VOUT: write values.  ValGen produces the value of input record i.
-template <typename K, bool KOUT, bool VOUT, typename ValGen>
+// ghist[pass][256] -> exclusive scan over the digits of each pass, in place (one warp per pass)
+__global__ void __launch_bounds__(32 * kRsMaxPasses) rs_digit_scan_kernel(u32* __restrict__ ghist, int npass) {
+    const u32 p = warp_id(), l = lane_id();
+    if ((int)p >= npass) return;
+    u32* row = ghist + p * 256;
+    u32 carry = 0;
+    for (int base = 0; base < 256; base += 32) {
+        const u32 v = row[base + l];
+        const u32 incl = warp_scan_incl(v);
+        row[base + l] = carry + incl - v;
+        carry += __shfl_sync(kFullMask, incl, 31);
+    }
+}
+
+// ---- bulk async copy (TMA) of one contiguous run of global memory into shared memory, completion on an mbarrier
+BZ_D void rs_mbar_init(u64* mbar) {
+#if !defined(BZ_EMU)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((u32)__cvta_generic_to_shared(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+BZ_D void rs_bulk_load(void* smem_dst, const void* gmem_src, u32 bytes, u64* mbar) {   // bytes: multiple of 16, both 16-byte aligned
+#if !defined(BZ_EMU)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"((u32)__cvta_generic_to_shared(mbar))
+                 : "memory");
+#endif
+}
+BZ_D void rs_mbar_expect(u64* mbar, u32 bytes) {
+#if !defined(BZ_EMU)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(mbar)), "r"(bytes) : "memory");
+#endif
+}
+BZ_D void rs_mbar_wait(u64* mbar, u32 parity) {
+#if !defined(BZ_EMU)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "RS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra RS_DONE;\n\t"
+        "bra RS_WAIT;\n\t"
+        "RS_DONE:\n\t"
+        "}" ::"r"((u32)__cvta_generic_to_shared(mbar)), "r"(parity) : "memory");
+#endif
+}
+
+BZ_D u32 rs_ld_desc(const u32* p) {
+#if defined(BZ_EMU)
+    return *reinterpret_cast<const volatile u32*>(p);
+#else
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+BZ_D void rs_st_desc(u32* p, u32 v) {
+#if defined(BZ_EMU)
+    *reinterpret_cast<volatile u32*>(p) = v;
+#else
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+
+// One stable pass on digit bits [shift, shift+bits).  KOUT: write keys;  VOUT: write values.  ValGen produces the value of
+// input record i; VTMA: the values are an array (ValFromArray) and come in by bulk copy like the keys.
+// desc[tile][256] (zeroed), ticket (zeroed), gbase[256] = first output slot of every digit.
+template <typename K, bool KOUT, bool VOUT, bool VTMA, typename ValGen>
 __global__ void __launch_bounds__(kRsThreads, BZ_RS_MIN_BLOCKS)
-rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, u32* __restrict__ vout, u32 n,
-                  int shift, u32 mask, const u32* __restrict__ bases, u32 ntiles) {
+rs_onesweep_kernel(const K* __restrict__ kin, ValGen vgen, const u32* __restrict__ vin, K* __restrict__ kout, u32* __restrict__ vout, u32 n,
+                   int shift, u32 mask, const u32* __restrict__ gbase, u32* __restrict__ desc, u32* __restrict__ ticket) {
     constexpr int ITEMS = RsCfg<K>::kItems;
     constexpr u32 TILE = kRsThreads * ITEMS;
     BZ_DYN_SMEM(unsigned char, rs_smem);
     u32* warp_cnt = reinterpret_cast<u32*>(rs_smem);              // [kRsWarps][256]
     u32* lbase = warp_cnt + kRsWarps * 256;                       // [256] first sorted slot of digit in tile
     u32* gdelta = lbase + 256;                                    // [256] global index minus tile slot
-    u32* svals = gdelta + 256;                                    // [TILE]
-    K* skeys = reinterpret_cast<K*>(svals + TILE);                // [TILE]
+    u32* svals = gdelta + 256;                                    // [TILE]  (bulk copy target, then sorted staging)
+    K* skeys = reinterpret_cast<K*>(svals + TILE);                // [TILE]  (16-byte aligned: TILE * 4 is a multiple of 16)
+    __shared__ u32 s_tile;
+    __shared__ u64 s_mbar;   // 8-byte aligned by its type
     const u32 w = warp_id(), l = lane_id();
-    const u32 tile_base = blockIdx.x * TILE;
-    const u32 count = min(TILE, n - tile_base);
 
+    if (threadIdx.x == 0) {
+        s_tile = atomicAdd(ticket, 1u);   // tiles start in ticket order: every tile before this one is running or done
+        rs_mbar_init(&s_mbar);
+    }
     for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) warp_cnt[i] = 0;
     __syncthreads();
+    const u32 tile = s_tile;
+    const u32 tile_base = tile * TILE;
+    const u32 count = min(TILE, n - tile_base);
 
     K key[ITEMS];
     u32 val[VOUT ? ITEMS : 1];
     u16 rank[ITEMS];
     const u32 base = tile_base + w * (32 * ITEMS);
     const u32 lt = lanemask_lt();
-    // all loads of the tile are issued before anything consumes them (memory-level parallelism: the
-    // v0 profile showed 60 % long-scoreboard stalls with the value loads serialised behind shared stores)
+#if !defined(BZ_EMU)
+    {   // the tile comes in by bulk async copies (the arrays are padded to 256 bytes, so rounding the last tile up to 16 is safe)
+        if (threadIdx.x == 0) {
+            const u32 kb = (count * (u32)sizeof(K) + 15u) & ~15u;
+            const u32 vb = (VOUT && VTMA) ? ((count * 4u + 15u) & ~15u) : 0u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            rs_mbar_expect(&s_mbar, kb + vb);
+            rs_bulk_load(skeys, kin + tile_base, kb, &s_mbar);
+            if (VOUT && VTMA) rs_bulk_load(svals, vin + tile_base, vb, &s_mbar);
+        }
+        rs_mbar_wait(&s_mbar, 0u);
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const u32 j = w * (32 * ITEMS) + it * 32 + l;
+            key[it] = (j < count) ? skeys[j] : (K)0;
+            if (VOUT) val[it] = (j < count) ? (VTMA ? svals[j] : vgen(tile_base + j)) : 0u;
+        }
+    }
+#else
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
         u32 i = base + it * 32 + l;
         key[it] = (i < n) ? kin[i] : (K)0;
         if (VOUT) val[it] = (i < n) ? vgen(i) : 0u;
     }
+#endif
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
         u32 i = base + it * 32 + l;
@@ -131,7 +245,7 @@ rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, 
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive scan over warps, then exclusive scan over digits
+    // per digit: exclusive scan over warps, the tile's count -> descriptor, look-back, exclusive scan over digits
     {
         const u32 d = threadIdx.x;
         u32 s = 0;
@@ -144,6 +258,23 @@ rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, 
         // digit 255 also holds the padding records of a partial tile; exclude them from the real count
         u32 real = s;
         if (d == 255) real -= (TILE - count);
+        u32* mine = desc + (size_t)tile * 256 + d;
+        rs_st_desc(mine, real | (tile == 0 ? kRsFlagInc : kRsFlagAgg));
+        u32 before = 0;   // records with this digit in the tiles before this one
+        if (tile > 0) {
+            const u32* p = mine;
+            for (u32 t = tile; t > 0; t--) {
+                p -= 256;
+                u32 v;
+                do {
+                    v = rs_ld_desc(p);
+                    BZ_SPIN_HINT();
+                } while ((v >> 30) == 0u);
+                before += v & kRsValMask;
+                if (v & kRsFlagInc) break;
+            }
+            rs_st_desc(mine, (before + real) | kRsFlagInc);
+        }
         u32 incl = warp_scan_incl(real);
         __shared__ u32 wsum[kRsWarps];
         if (l == 31) wsum[w] = incl;
@@ -154,7 +285,7 @@ rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, 
             if ((u32)k < w) wp += wsum[k];
         u32 excl = wp + incl - real;
         lbase[d] = excl;
-        gdelta[d] = bases[d * ntiles + blockIdx.x] - excl;
+        gdelta[d] = gbase[d] + before - excl;
     }
     __syncthreads();
 #pragma unroll
@@ -182,59 +313,6 @@ rs_scatter_kernel(const K* __restrict__ kin, ValGen vgen, K* __restrict__ kout, 
     }
 }
 
-// Exclusive scan of hist[256][ntiles] in digit-major order in two launches (one CTA per digit row):
-// row totals first, then every row scans itself starting from the sum of the rows before it.
-__global__ void __launch_bounds__(256) rs_row_total_kernel(const u32* __restrict__ hist, u32 ntiles, u32* __restrict__ row_total) {
-    __shared__ u32 red[8];
-    const u32* row = hist + (size_t)blockIdx.x * ntiles;
-    u32 s = 0;
-    for (u32 i = threadIdx.x; i < ntiles; i += 256) s += row[i];
-    s = warp_reduce_sum(s);
-    if (lane_id() == 0) red[warp_id()] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 t = 0;
-        for (int k = 0; k < 8; k++) t += red[k];
-        row_total[blockIdx.x] = t;
-    }
-}
-__global__ void __launch_bounds__(256) rs_row_scan_kernel(u32* __restrict__ hist, u32 ntiles, const u32* __restrict__ row_total) {
-    __shared__ u32 wsum[8];
-    __shared__ u32 carry_s;
-    const u32 d = blockIdx.x;
-    {   // sum of the totals of rows 0..d-1 (256 values)
-        u32 v = threadIdx.x < d ? row_total[threadIdx.x] : 0u;
-        v = warp_reduce_sum(v);
-        if (lane_id() == 0) wsum[warp_id()] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u32 t = 0;
-            for (int k = 0; k < 8; k++) t += wsum[k];
-            carry_s = t;
-        }
-        __syncthreads();
-    }
-    u32* row = hist + (size_t)d * ntiles;
-    u32 carry = carry_s;
-    for (u32 base = 0; base < ntiles; base += 256) {
-        const u32 i = base + threadIdx.x;
-        const u32 v = i < ntiles ? row[i] : 0u;
-        const u32 incl = warp_scan_incl(v);
-        __syncthreads();  // wsum reuse
-        if (lane_id() == 31) wsum[warp_id()] = incl;
-        __syncthreads();
-        u32 wp = 0, tot = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const u32 t = wsum[k];
-            if ((u32)k < warp_id()) wp += t;
-            tot += t;
-        }
-        if (i < ntiles) row[i] = carry + wp + incl - v;
-        carry += tot;
-    }
-}
-
 template <typename K>
 inline u32 rs_num_tiles(u32 n) {
     constexpr u32 TILE = kRsThreads * RsCfg<K>::kItems;
@@ -245,34 +323,59 @@ inline size_t rs_scatter_smem() {
     constexpr u32 TILE = kRsThreads * RsCfg<K>::kItems;
     return (size_t)(kRsWarps * 256 + 512) * 4 + (size_t)TILE * 4 + (size_t)TILE * sizeof(K);
 }
-// scratch (in u32 elements) for one pass over n records
+// scratch (in u32 elements) for a sort of n records: descriptors of one pass, histograms of all passes, ticket
 template <typename K>
 inline size_t rs_temp_elems(u32 n) {
-    size_t h = (size_t)256 * rs_num_tiles<K>(n);
-    return h + 256 /* row totals */ + scan_temp_elems((u32)h) + 16;
+    return (size_t)256 * rs_num_tiles<K>(n) + 256 * kRsMaxPasses + 64;
 }
 
-// One stable pass on digit bits [shift, shift+bits).
-template <typename K, bool KOUT, bool VOUT, typename ValGen>
-cudaError_t rs_pass(cudaStream_t st, const K* kin, ValGen vgen, K* kout, u32* vout, u32 n, int shift, int bits,
-                    u32* temp) {
-    if (n == 0) return cudaSuccess;
+// temp layout
+template <typename K>
+struct RsTemp {
+    u32* desc;
+    u32* ghist;
+    u32* ticket;
+    RsTemp(u32* temp, u32 n) : desc(temp), ghist(temp + (size_t)256 * rs_num_tiles<K>(n)), ticket(ghist + 256 * kRsMaxPasses) {}
+};
+
+// histograms of all passes of a sort on key bits [0, nbits) -> gbase[pass][digit] in T.ghist
+template <typename K>
+cudaError_t rs_histograms(cudaStream_t st, const K* keys, u32 n, int nbits, const RsTemp<K>& T) {
+    const int npass = (nbits + 7) / 8;
+    BZ_CUDA_TRY(cudaMemsetAsync(T.ghist, 0, sizeof(u32) * 256 * kRsMaxPasses, st));
+    const u32 chunks = (n + kRsThreads * 8 - 1) / (kRsThreads * 8);
+    const u32 grid = chunks < 148u * 8u ? chunks : 148u * 8u;
+    BZ_LAUNCH(grid, kRsThreads, 0, st, rs_hist_all_kernel<K>)(keys, n, nbits, T.ghist); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(1, 32 * kRsMaxPasses, 0, st, rs_digit_scan_kernel)(T.ghist, npass); BZ_NOTE_LAUNCH();
+    BZ_CUDA_TRY(cudaGetLastError());
+    return cudaSuccess;
+}
+
+// One stable pass on digit bits [shift, shift+bits); T.ghist + 256 * pass_index must hold the digit bases of this pass.
+template <typename K, bool KOUT, bool VOUT, bool VTMA, typename ValGen>
+cudaError_t rs_pass_sweep(cudaStream_t st, const K* kin, ValGen vgen, const u32* vin, K* kout, u32* vout, u32 n, int shift, int bits,
+                          int pass_index, const RsTemp<K>& T) {
     const u32 ntiles = rs_num_tiles<K>(n);
     const u32 mask = (1u << bits) - 1u;
-    u32* hist = temp;
-    BZ_LAUNCH(ntiles, kRsThreads, 0, st, rs_tile_hist_kernel<K>)(kin, n, shift, mask, hist, ntiles); BZ_NOTE_LAUNCH();
-    BZ_CUDA_TRY(cudaGetLastError());
-    const u32 hn = 256 * ntiles;
-    BZ_LAUNCH(256, 256, 0, st, rs_row_total_kernel)(hist, ntiles, hist + hn); BZ_NOTE_LAUNCH();
-    BZ_LAUNCH(256, 256, 0, st, rs_row_scan_kernel)(hist, ntiles, hist + hn); BZ_NOTE_LAUNCH();
-    BZ_CUDA_TRY(cudaGetLastError());
-    auto kern = rs_scatter_kernel<K, KOUT, VOUT, ValGen>;
+    BZ_CUDA_TRY(cudaMemsetAsync(T.desc, 0, sizeof(u32) * 256 * (size_t)ntiles, st));
+    BZ_CUDA_TRY(cudaMemsetAsync(T.ticket, 0, sizeof(u32), st));
+    auto kern = rs_onesweep_kernel<K, KOUT, VOUT, VTMA, ValGen>;
     const size_t smem = rs_scatter_smem<K>();
     // set every time: the attribute is per device and a process may drive several GPUs
     BZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BZ_LAUNCH(ntiles, kRsThreads, smem, st, kern)(kin, vgen, kout, vout, n, shift, mask, hist, ntiles); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(ntiles, kRsThreads, smem, st, kern)(kin, vgen, vin, kout, vout, n, shift, mask, T.ghist + 256 * pass_index, T.desc, T.ticket);
+    BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     return cudaSuccess;
+}
+
+// A single stable pass (the psi construction of the inverse BWT): histogram + one sweep.
+template <typename K, bool KOUT, bool VOUT, typename ValGen>
+cudaError_t rs_pass(cudaStream_t st, const K* kin, ValGen vgen, K* kout, u32* vout, u32 n, int shift, int bits, u32* temp) {
+    if (n == 0) return cudaSuccess;
+    RsTemp<K> T(temp, n);
+    BZ_CUDA_TRY(rs_histograms<K>(st, kin, n, shift + bits, T));
+    return rs_pass_sweep<K, KOUT, VOUT, false, ValGen>(st, kin, vgen, nullptr, kout, vout, n, shift, bits, shift / 8, T);
 }
 
 // Full LSD sort of (key, value) records on key bits [0, nbits).  Ping-pongs between the A and B
@@ -282,6 +385,9 @@ template <typename K>
 cudaError_t rs_sort_pairs(cudaStream_t st, K* ka, u32* va, K* kb, u32* vb, u32 n, int nbits, u32* temp,
                           bool* result_in_b, bool vals_are_index = false) {
     bool in_b = false;
+    if (n == 0) { *result_in_b = false; return cudaSuccess; }
+    RsTemp<K> T(temp, n);
+    BZ_CUDA_TRY(rs_histograms<K>(st, ka, n, nbits, T));
     for (int shift = 0; shift < nbits; shift += 8) {
         int bits = nbits - shift < 8 ? nbits - shift : 8;
         K* src_k = in_b ? kb : ka;
@@ -289,10 +395,11 @@ cudaError_t rs_sort_pairs(cudaStream_t st, K* ka, u32* va, K* kb, u32* vb, u32 n
         K* dst_k = in_b ? ka : kb;
         u32* dst_v = in_b ? va : vb;
         if (shift == 0 && vals_are_index) {
-            BZ_CUDA_TRY((rs_pass<K, true, true, ValIdentity>(st, src_k, ValIdentity{}, dst_k, dst_v, n, shift, bits, temp)));
+            BZ_CUDA_TRY((rs_pass_sweep<K, true, true, false, ValIdentity>(st, src_k, ValIdentity{}, nullptr, dst_k, dst_v, n, shift, bits,
+                                                                        shift / 8, T)));
         } else {
-            BZ_CUDA_TRY((rs_pass<K, true, true, ValFromArray>(st, src_k, ValFromArray{src_v}, dst_k, dst_v, n, shift,
-                                                              bits, temp)));
+            BZ_CUDA_TRY((rs_pass_sweep<K, true, true, true, ValFromArray>(st, src_k, ValFromArray{src_v}, src_v, dst_k, dst_v, n, shift,
+                                                                        bits, shift / 8, T)));
         }
         in_b = !in_b;
     }

@@ -28,15 +28,6 @@ EXPORT int emu_cm_decode(const uint8_t* in, int32_t insize, uint8_t* out, int32_
     return 0;
 }
 
-EXPORT int32_t emu_lzp_encode(const uint8_t* in, int32_t n, uint8_t* out, int32_t* lut) {
-    s32 res = -12345;
-    emu::Dim3 g, b;
-    b.x = 32;
-    memset(lut, 0, sizeof(int32_t) << kLzpSlotsLog2);
-    emu::launch(g, b, 0, [&] { lzp_encode_warp_kernel(in, n, out, lut, &res); });
-    return res;
-}
-
 EXPORT int32_t emu_lzp_decode(const uint8_t* in, int32_t n, uint8_t* out, int32_t max, int32_t* lut) {
     s32 res = -12345;
     emu::Dim3 g, b;

@@ -1,4 +1,4 @@
-// emu_stages.cpp -- the multi-kernel stages (CRC, mRLE, suffix-array BWT, inverse BWT) on the CPU thread-block
+// emu_stages.cpp -- the multi-kernel stages (CRC, mRLE, LZP encoder, suffix-array BWT, inverse BWT) on the CPU thread-block
 // emulator: the REAL host-side launch sequences of bzip3_b200/csrc/*.cuh (scan / radix sort / prefix doubling ...)
 // compiled by g++ against tests/native/cta_emu.h, where a launch runs the grid to completion, "device" memory is
 // host memory and a stream is synchronous.  Buffers are carved like bz3_api.cu carves its arena.
@@ -15,6 +15,7 @@
 #include "../../bzip3_b200/csrc/mrle.cuh"
 #include "../../bzip3_b200/csrc/sufsort.cuh"
 #include "../../bzip3_b200/csrc/unbwt.cuh"
+#include "../../bzip3_b200/csrc/lzp_scan.cuh"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -112,4 +113,23 @@ EXPORT int emu_stage_unbwt(const uint8_t* in, uint32_t n, int32_t idx, uint8_t* 
     int status = -12345;
     if (unbwt(nullptr, src, n, idx, out, B, &status) != cudaSuccess) return -777;
     return status;
+}
+
+EXPORT int32_t emu_stage_lzp_encode(const uint8_t* in, int32_t n, uint8_t* out) {
+    if (n < kLzpMinMatch + 32) return -1;
+    Pool P;
+    LzpScanBuffers B;
+    const u32 m = (u32)n - 4u;
+    for (int i = 0; i < 2; i++) B.key[i] = P.take<u32>(m);
+    for (int i = 0; i < 2; i++) B.idx[i] = P.take<u32>(m);
+    B.P = P.take<u32>((size_t)n + 8);
+    B.code = P.take<u8>((size_t)n + 8);
+    B.skipbits = P.take<u32>((size_t)(n + 31) / 32 + 1);
+    B.temp = P.take<u32>(rs_temp_elems<u32>(m));
+    u8* src = P.take<u8>((size_t)n + 64);
+    memcpy(src, in, (size_t)n);
+    s32* res = P.take<s32>(4);
+    *res = -12345;
+    if (lzp_scan_encode(nullptr, src, n, out, B, res) != cudaSuccess) return -777;
+    return *res;
 }

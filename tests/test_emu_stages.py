@@ -18,7 +18,7 @@ SO = os.path.join(ROOT, "tests", "_build", "libemustages.so")
 SRCS = [os.path.join(ROOT, "tests", "native", f) for f in ("emu_stages.cpp", "cta_emu.cpp")]
 DEPS = SRCS + [os.path.join(ROOT, "tests", "native", "cta_emu.h")] + [
     os.path.join(ROOT, "bzip3_b200", "csrc", f) for f in ("common.cuh", "scan.cuh", "radix_sort.cuh", "crc.cuh", "mrle.cuh",
-                                                          "sufsort.cuh", "unbwt.cuh")]
+                                                          "sufsort.cuh", "unbwt.cuh", "lzp.cuh", "lzp_scan.cuh")]
 _lib = None
 
 
@@ -40,6 +40,8 @@ def emu():
         L.emu_stage_bwt.argtypes = [refs.u8p, C.c_uint32, refs.u8p]
         L.emu_stage_unbwt.restype = C.c_int
         L.emu_stage_unbwt.argtypes = [refs.u8p, C.c_uint32, C.c_int32, refs.u8p]
+        L.emu_stage_lzp_encode.restype = C.c_int32
+        L.emu_stage_lzp_encode.argtypes = [refs.u8p, C.c_int32, refs.u8p]
         _lib = L
     return _lib
 
@@ -132,3 +134,38 @@ def test_unbwt_on_corrupt_input_matches_oracle():
     for bad in (0, -3, n + 1):
         got = np.zeros(n + 64, np.uint8)
         assert E.emu_stage_unbwt(refs.ptr(L0), n, bad, refs.ptr(got)) != 0
+
+
+def _lzp_cases():
+    rng = np.random.default_rng(5)
+    rep = np.tile(rng.integers(0, 256, 700, dtype=np.uint8), 60)          # long matches, period 700
+    runs = np.repeat(rng.integers(0, 3, 300, dtype=np.uint8), 150)        # every context repeats, matches back to back
+    esc = rng.choice(np.array([0xF2, 0x41, 0x42], np.uint8), 30000)       # escape bytes with live slots
+    mix = np.concatenate([rep[:9000], rng.integers(0, 256, 5000, dtype=np.uint8), rep[:9000], runs[:6000], esc[:4000]])
+    near = synth.source_corpus(40 << 10, seed=31)
+    dup = np.concatenate([near, rng.integers(0, 256, 3000, dtype=np.uint8), near[5000:30000], near[:9000]])   # far repeats
+    extra = [("periodic_42k", rep), ("runs_45k", runs), ("escapes_30k", esc), ("mix_33k", mix), ("far_repeats_77k", dup),
+             ("source_96k", synth.source_corpus(96 << 10, seed=21)), ("log_64k", synth.log_stream(64 << 10, seed=22)),
+             ("zipf_64k", synth.zipf_text(64 << 10, seed=23))]
+    return CASES + [(n, np.ascontiguousarray(d)) for n, d in extra]
+
+
+LZP_CASES = _lzp_cases()
+
+
+@pytest.mark.parametrize("name,data", LZP_CASES, ids=[c[0] for c in LZP_CASES])
+def test_lzp_scan_encoder(name, data):
+    """hash keys -> sort -> links -> candidate codes -> commit engine, against the oracle's lzp_encode_block"""
+    E, O = emu(), refs.oracle()
+    n = len(data)
+    pad = np.zeros(n + 64, np.uint8)
+    pad[:n] = data
+    want = np.zeros(n + 64, np.uint8)
+    got = np.zeros(n + 64, np.uint8)
+    lut = np.zeros(1 << 18, np.int32)
+    rw = O.orc_lzp_encode(refs.ptr(pad), n, refs.ptr(want), lut.ctypes.data_as(refs.i32p))
+    rg = E.emu_stage_lzp_encode(refs.ptr(pad), n, refs.ptr(got))
+    assert rg == rw, (rg, rw)
+    if rw > 0:
+        d = np.nonzero(got[:rw] != want[:rw])[0]
+        assert len(d) == 0, ("first difference at", int(d[0]), "of", rw)
