@@ -240,7 +240,7 @@ size_t sufsort_arena_bytes(size_t n) {
            align_up(4 * sufsort_temp_elems((u32)n)) + 16 * kAlign;
 }
 size_t lzp_arena_bytes(size_t n) {
-    return 4 * align_up(4 * n) + align_up(4 * (n + 8)) + align_up(n + 8) + align_up(4 * ((n + 31) / 32 + 1)) +
+    return 4 * align_up(4 * n) + align_up(4 * (n + 8)) + align_up(n + 8) +
            align_up(4 * rs_temp_elems<u32>((u32)n)) + 16 * kAlign;
 }
 size_t other_arena_bytes(size_t n) {
@@ -350,7 +350,7 @@ cudaError_t run_lzp_encode(bz3_state* s, const u8* d_in, s32 n, u8* d_out, s32* 
     for (int i = 0; i < 2; i++) B.idx[i] = A.take<u32>(m);
     B.P = A.take<u32>((size_t)n + 8);
     B.code = A.take<u8>((size_t)n + 8);
-    B.skipbits = A.take<u32>((size_t)(n + 31) / 32 + 1);
+    B.lut = s->d_lut;
     B.temp = A.take<u32>(rs_temp_elems<u32>(m));
     if (!B.temp) return cudaErrorMemoryAllocation;
     s32* d_res = reinterpret_cast<s32*>(s->d_scal + 8);

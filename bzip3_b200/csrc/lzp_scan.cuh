@@ -15,14 +15,16 @@
 //                            nothing had been skipped; one byte per position: 0 = no candidate, k = 4k bytes match
 //                            (10 = "at least LZP_MIN_MATCH")
 //   in order (one thread block, 1024 positions per step)
-//     lzp_commit_kernel      walks the input once.  A step loads P / code / the byte of 1024 consecutive positions,
-//                            repairs the few lanes whose predecessor was skipped by an earlier match (bitmap of skipped
-//                            positions, coarse summary in shared memory; the lane follows P until a visited position
-//                            and re-does quick check and length against it), lets one thread run the reference's
-//                            candidate logic (`heur` veto, :145, :152-155) over the lanes that passed the quick check,
-//                            and emits literals with a block-wide prefix sum.  An accepted match is measured to its
-//                            full length by all threads, its token written, its interior marked skipped, and the walk
-//                            restarts behind it.
+//     lzp_commit_kernel      walks the input once and keeps the reference's table (last visited position per hash) for
+//                            everything BEFORE the current literal run.  A step loads P / code / the byte of 1024
+//                            consecutive positions.  A lane whose predecessor P[i] lies inside the run sees exactly P[i]
+//                            in the reference's table (every position of the run was visited); any other lane reads the
+//                            table, and only if that differs from P[i] (the predecessor was skipped by an earlier match)
+//                            re-does quick check and length against it.  One warp then runs the reference's candidate
+//                            logic (`heur` veto, :145, :152-155) over the lanes that passed the quick check, literals
+//                            are emitted with a block-wide prefix sum and the visited positions enter the table
+//                            (order-free: positions only grow, atomicMax).  An accepted match is measured to its full
+//                            length by all threads, its token written, and the walk restarts behind it.
 // Text without long repeats never leaves the streaming path: the commit engine then moves ~1 byte per clock.  Data that
 // is one match after the other pays one step (a few dependent memory round trips) per match, like the reference pays a
 // cache miss per match.
@@ -37,7 +39,6 @@ namespace bz3 {
 
 constexpr int kLzpEngThreads = 1024;
 constexpr int kLzpEngWarps = kLzpEngThreads / 32;
-constexpr int kLzpCoarseShift = 12;   // one summary bit per 4096 positions
 
 BZ_D u32 lzp_word(const u8* __restrict__ p) {
     return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
@@ -81,13 +82,30 @@ __global__ void __launch_bounds__(256) lzp_link_kernel(const u32* __restrict__ s
     P[sidx[j] + 4u] = prev;
 }
 
+// the ten 32-bit words at p, p+4, .. p+36 (any alignment) from eleven aligned loads that are all in flight together
+BZ_D void lzp_load10(const u8* __restrict__ in, s32 p, u32 (&w)[10]) {
+    const u32* a = reinterpret_cast<const u32*>(in + (p & ~3));
+    const int sh = 8 * (p & 3);
+    u32 x[11];
+#pragma unroll
+    for (int k = 0; k < 11; k++) x[k] = a[k];
+#pragma unroll
+    for (int k = 0; k < 10; k++) w[k] = sh ? __funnelshift_r(x[k], x[k + 1], sh) : x[k];
+}
+
 // quick check and capped word-wise length of position p against reference position r (:143-150).  0 = the quick check
-// fails; k in 1..10 = 4k bytes match (10: at least LZP_MIN_MATCH).  p < scan_end.
+// fails; k in 1..10 = 4k bytes match (10: at least LZP_MIN_MATCH).  p < scan_end.  All loads are issued before the first
+// compare (the word loop of the reference is a chain of dependent loads otherwise).
 BZ_D u32 lzp_candidate_code(const u8* __restrict__ in, s32 p, s32 r, s32 scan_end) {
     if (lzp_word(in + p) != lzp_word(in + r)) return 0u;
-    if (lzp_word(in + p + kLzpMinMatch - 4) != lzp_word(in + r + kLzpMinMatch - 4)) return 0u;
+    u32 a[10], b[10];
+    lzp_load10(in, p, a);
+    lzp_load10(in, r, b);
+    if (a[9] != b[9]) return 0u;   // bytes 36..39
     s32 len = 4;
-    while (len < kLzpMinMatch && p + len < scan_end && lzp_word(in + p + len) == lzp_word(in + r + len)) len += 4;
+#pragma unroll
+    for (int k = 1; k < 10; k++)
+        if (len == 4 * k && p + len < scan_end && a[k] == b[k]) len += 4;
     return (u32)len >> 2;
 }
 
@@ -110,42 +128,65 @@ struct LzpEngShared {
     u32 first_stop;
 };
 
-BZ_D bool lzp_is_skipped(const u32* __restrict__ skipbits, s32 pos) { return (__ldcg(&skipbits[pos >> 5]) >> (pos & 31)) & 1u; }
-
 // in: n bytes (readable, zero or not, up to n + 32).  P, code: from the kernels above (code zero outside [4, scan_end)).
-// skipbits: (n + 31) / 32 words, zeroed.  dynamic shared memory: coarse summary, ((n >> 12) + 32) / 32 words.
+// lut: the 2^18-entry table, zeroed.
 __global__ void __launch_bounds__(kLzpEngThreads, 1) lzp_commit_kernel(const u8* __restrict__ in, s32 n, const u32* __restrict__ P,
-                                                                      const u8* __restrict__ code, u32* __restrict__ skipbits,
+                                                                      const u8* __restrict__ code, s32* __restrict__ lut,
                                                                       u8* __restrict__ out, s32* __restrict__ result) {
-    BZ_DYN_SMEM(u32, coarse);
     __shared__ LzpEngShared S;
     const int t = threadIdx.x;
     const u32 lane = lane_id(), warp = warp_id();
     const s32 out_stop = n - 8;
     const s32 scan_end = n - kLzpMinMatch - 32;
-    for (int k = t; k < ((n >> kLzpCoarseShift) + 32) / 32; k += kLzpEngThreads) coarse[k] = 0;
     if (t < 4) out[t] = in[t];
     if (t == 0) S.heur = 0;
     __syncthreads();
     s32 ip = 4, op = 4;
     s32 run_start = 4;   // first position behind the last match: everything in [run_start, ip) was visited
+    s32 pf_ip = -1, pf_val = 0;   // prefetched window (start position; this lane's values)
+    u32 pf_c = 0, pf_h = 0;
+    u8 pf_b = 0;
+    s32 wcap = kLzpEngThreads;   // positions per step: shrinks where one match follows the other (the lanes behind a match are
+                                 // thrown away), doubles again while no match is found
     for (int phase = 0; phase < 2; phase++) {   // 0: positions that may start a match; 1: the literal-only tail (:187-195)
         const s32 limit = phase == 0 ? scan_end : n;
         while (ip < limit && op < out_stop) {
-            const s32 W = (limit - ip) < kLzpEngThreads ? (limit - ip) : kLzpEngThreads;
+            const s32 W = (limit - ip) < wcap ? (limit - ip) : wcap;
             const bool active = t < W;
             const s32 p = ip + t;
             s32 val = 0;
-            u32 c = 0;
+            u32 c = 0, h = 0;
             u8 b = 0;
             if (active) {
-                b = in[p];
-                val = (s32)P[p];
-                c = phase == 0 ? code[p] : 0u;
-                if (val > 0 && val < run_start && ((coarse[val >> (kLzpCoarseShift + 5)] >> ((val >> kLzpCoarseShift) & 31)) & 1u) &&
-                    lzp_is_skipped(skipbits, val)) {
-                    // the all-positions predecessor was never inserted: the table holds the nearest visited one
-                    do val = (s32)P[val]; while (val > 0 && lzp_is_skipped(skipbits, val));
+                if (pf_ip == ip) {   // this window was requested one step ago
+                    b = pf_b;
+                    val = pf_val;
+                    c = pf_c;
+                    h = pf_h;
+                } else {
+                    b = in[p];
+                    val = (s32)P[p];
+                    c = phase == 0 ? code[p] : 0u;
+                    h = lzp_hash(lzp_context(in, p));
+                }
+            }
+            {   // request the next full window now (the common case: no match in this one); it is consumed a step later
+                const s32 np = ip + W + t;
+                if (W == kLzpEngThreads && np < limit) {
+                    pf_b = in[np];
+                    pf_val = (s32)P[np];
+                    pf_c = phase == 0 ? code[np] : 0u;
+                    pf_h = lzp_hash(lzp_context(in, np));
+                    pf_ip = ip + W;
+                } else {
+                    pf_ip = -1;
+                }
+            }
+            if (active && val > 0 && val < run_start) {
+                // predecessor from before the run: the table knows whether it was ever inserted
+                const s32 tv = __ldcg(&lut[h]);
+                if (tv != val) {   // it was skipped by a match: the table holds an older visited position (or none)
+                    val = tv;
                     c = (phase == 0 && val > 0) ? lzp_candidate_code(in, p, val, scan_end) : 0u;
                 }
             }
@@ -206,6 +247,8 @@ __global__ void __launch_bounds__(kLzpEngThreads, 1) lzp_commit_kernel(const u8*
                 if (esc && o + 1 < n) out[o + 1] = 255;
             }
             op += (s32)total;
+            // the visited positions (literals and the match position itself) enter the table; the last one of a hash wins
+            if (active && t <= (match_lane >= 0 ? match_lane : W - 1)) atomicMax(&lut[h], p);
             if (match_lane >= 0) {
                 const s32 m = ip + match_lane, r = S.sval[match_lane];
                 // full length, word-wise while m + len < scan_end (:147-150); the first 40 bytes are known to match
@@ -240,23 +283,13 @@ __global__ void __launch_bounds__(kLzpEngThreads, 1) lzp_commit_kernel(const u8*
                     if (op + 1 + k < n) out[op + 1 + k] = 254;
                 if (t == 0 && op + 1 + q < n) out[op + 1 + q] = (u8)(codev - 254 * q);
                 op += 2 + q;
-                // positions m+1 .. m+len-1 are never inserted into the table
-                const s32 a = m + 1, e = m + len;   // [a, e)
-                if (a < e) {
-                    const s32 wa = a >> 5, we = (e - 1) >> 5;
-                    for (s32 wi = wa + t; wi <= we; wi += kLzpEngThreads) {
-                        u32 bits = 0xFFFFFFFFu;
-                        if (wi == wa) bits &= 0xFFFFFFFFu << (a & 31);
-                        if (wi == we) bits &= 0xFFFFFFFFu >> (31 - ((e - 1) & 31));
-                        atomicOr(&skipbits[wi], bits);
-                    }
-                    const s32 ca = a >> kLzpCoarseShift, ce = (e - 1) >> kLzpCoarseShift;
-                    for (s32 ci = ca + t; ci <= ce; ci += kLzpEngThreads) atomicOr(&coarse[ci >> 5], 1u << (ci & 31));
-                }
                 ip = m + len;
                 run_start = ip;
+                wcap = 128;
+                while (wcap < 2 * (match_lane + 1) && wcap < kLzpEngThreads) wcap *= 2;
             } else {
                 ip += W;
+                if (wcap < kLzpEngThreads) wcap *= 2;
             }
             __syncthreads();
         }
@@ -272,10 +305,9 @@ struct LzpScanBuffers {
     u32* idx[2];   // [m] each
     u32* P;        // [n + 8]
     u8* code;      // [n + 8]
-    u32* skipbits; // [(n + 31) / 32 + 1]
+    s32* lut;      // [2^18], zeroed by lzp_scan_encode
     u32* temp;     // rs_temp_elems<u32>(m)
 };
-inline size_t lzp_scan_smem(s32 n) { return (size_t)(((n >> kLzpCoarseShift) + 32) / 32 + 1) * 4; }
 
 // in: device, n bytes, 16-byte aligned, readable up to n + 32.  *result (device) = encoded size or -1.
 inline cudaError_t lzp_scan_encode(cudaStream_t st, const u8* in, s32 n, u8* out, const LzpScanBuffers& B, s32* d_result) {
@@ -289,14 +321,12 @@ inline cudaError_t lzp_scan_encode(cudaStream_t st, const u8* in, s32 n, u8* out
     BZ_CUDA_TRY(cudaMemsetAsync(B.P, 0, sizeof(u32) * 8, st));   // positions 0..3 have no context
     BZ_LAUNCH((m + 255) / 256, 256, 0, st, lzp_link_kernel)(B.key[sc], B.idx[sc], m, B.P); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaMemsetAsync(B.code, 0, (size_t)n + 8, st));
-    BZ_CUDA_TRY(cudaMemsetAsync(B.skipbits, 0, sizeof(u32) * ((size_t)(n + 31) / 32 + 1), st));
+    BZ_CUDA_TRY(cudaMemsetAsync(B.lut, 0, sizeof(s32) * kLzpSlots, st));
     if (scan_end > 4) {
         BZ_LAUNCH((u32)(scan_end - 4 + 255) / 256, 256, 0, st, lzp_code_kernel)(in, B.P, scan_end, B.code); BZ_NOTE_LAUNCH();
     }
     BZ_CUDA_TRY(cudaGetLastError());
-    const size_t smem = lzp_scan_smem(n);
-    BZ_CUDA_TRY(cudaFuncSetAttribute(lzp_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BZ_LAUNCH(1, kLzpEngThreads, smem, st, lzp_commit_kernel)(in, n, B.P, B.code, B.skipbits, out, d_result); BZ_NOTE_LAUNCH();
+    BZ_LAUNCH(1, kLzpEngThreads, 0, st, lzp_commit_kernel)(in, n, B.P, B.code, B.lut, out, d_result); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     return cudaSuccess;
 }

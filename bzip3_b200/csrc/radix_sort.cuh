@@ -64,13 +64,21 @@ constexpr u32 kRsFlagInc = 2u << 30;   // descriptor holds the inclusive prefix 
 constexpr u32 kRsValMask = (1u << 30) - 1u;   // n < 2^30 (blocks are at most 511 MiB + 2 %)
 constexpr int kRsMaxPasses = 8;
 
-// digit histograms of all passes in one read of the keys: ghist[pass][256] (zeroed by the caller)
+// digit histograms of all passes in one read of the keys: ghist[pass][256] (zeroed by the caller).  Every warp keeps
+// private counters for all passes in shared memory across all the chunks its block walks (grid-stride); one reduction
+// and one round of global atomics per block at the end.
+constexpr int kRsHistItems = 8;
+inline size_t rs_hist_smem(int npass) { return (size_t)kRsWarps * npass * 256 * sizeof(u32); }
+
 template <typename K>
 __global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const K* __restrict__ keys, u32 n, int nbits, u32* __restrict__ ghist) {
-    constexpr int ITEMS = 8;
-    __shared__ u32 cnt[kRsWarps][256];
+    constexpr int ITEMS = kRsHistItems;
+    BZ_DYN_SMEM(u32, cnt);   // [kRsWarps][npass][256]
     const u32 w = warp_id(), l = lane_id();
     const int npass = (nbits + 7) / 8;
+    for (int i = threadIdx.x; i < kRsWarps * npass * 256; i += kRsThreads) cnt[i] = 0;
+    __syncthreads();
+    u32* mine = cnt + (size_t)w * npass * 256;
     for (u32 tile = blockIdx.x; (u64)tile * (kRsThreads * ITEMS) < n; tile += gridDim.x) {
         const u32 base = tile * (kRsThreads * ITEMS) + w * (32 * ITEMS);
         K key[ITEMS];
@@ -82,23 +90,19 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const K* __rest
         for (int p = 0; p < npass; p++) {
             const int shift = 8 * p;
             const u32 mask = (nbits - shift < 8) ? ((1u << (nbits - shift)) - 1u) : 255u;
-            for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) (&cnt[0][0])[i] = 0;
-            __syncthreads();
 #pragma unroll
             for (int it = 0; it < ITEMS; it++) {
                 const u32 i = base + it * 32 + l;
-                if (i < n) atomicAdd(&cnt[w][rs_digit(key[it], shift, mask)], 1u);
+                if (i < n) atomicAdd(&mine[p * 256 + rs_digit(key[it], shift, mask)], 1u);
             }
-            __syncthreads();
-            {
-                const u32 d = threadIdx.x;
-                u32 sum = 0;
-#pragma unroll
-                for (int k = 0; k < kRsWarps; k++) sum += cnt[k][d];
-                if (sum) atomicAdd(&ghist[p * 256 + d], sum);
-            }
-            __syncthreads();
         }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * 256; i += kRsThreads) {
+        u32 sum = 0;
+#pragma unroll
+        for (int k = 0; k < kRsWarps; k++) sum += cnt[(size_t)k * npass * 256 + i];
+        if (sum) atomicAdd(&ghist[i], sum);
     }
 }
 
@@ -169,7 +173,7 @@ BZ_D void rs_st_desc(u32* p, u32 v) {
 // One stable pass on digit bits [shift, shift+bits).  KOUT: write keys;  VOUT: write values.  ValGen produces the value of
 // input record i; VTMA: the values are an array (ValFromArray) and come in by bulk copy like the keys.
 // desc[tile][256] (zeroed), ticket (zeroed), gbase[256] = first output slot of every digit.
-template <typename K, bool KOUT, bool VOUT, bool VTMA, typename ValGen>
+template <typename K, bool KOUT, bool VOUT, bool VTMA, bool TMA, typename ValGen>
 __global__ void __launch_bounds__(kRsThreads, BZ_RS_MIN_BLOCKS)
 rs_onesweep_kernel(const K* __restrict__ kin, ValGen vgen, const u32* __restrict__ vin, K* __restrict__ kout, u32* __restrict__ vout, u32 n,
                    int shift, u32 mask, const u32* __restrict__ gbase, u32* __restrict__ desc, u32* __restrict__ ticket) {
@@ -201,7 +205,7 @@ rs_onesweep_kernel(const K* __restrict__ kin, ValGen vgen, const u32* __restrict
     const u32 base = tile_base + w * (32 * ITEMS);
     const u32 lt = lanemask_lt();
 #if !defined(BZ_EMU)
-    {   // the tile comes in by bulk async copies (the arrays are padded to 256 bytes, so rounding the last tile up to 16 is safe)
+    if (TMA) {   // the tile comes in by bulk async copies (the arrays are padded to 256 bytes, so rounding the last tile up to 16 is safe)
         if (threadIdx.x == 0) {
             const u32 kb = (count * (u32)sizeof(K) + 15u) & ~15u;
             const u32 vb = (VOUT && VTMA) ? ((count * 4u + 15u) & ~15u) : 0u;
@@ -217,15 +221,16 @@ rs_onesweep_kernel(const K* __restrict__ kin, ValGen vgen, const u32* __restrict
             key[it] = (j < count) ? skeys[j] : (K)0;
             if (VOUT) val[it] = (j < count) ? (VTMA ? svals[j] : vgen(tile_base + j)) : 0u;
         }
-    }
-#else
-#pragma unroll
-    for (int it = 0; it < ITEMS; it++) {
-        u32 i = base + it * 32 + l;
-        key[it] = (i < n) ? kin[i] : (K)0;
-        if (VOUT) val[it] = (i < n) ? vgen(i) : 0u;
-    }
+    } else
 #endif
+    {
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            u32 i = base + it * 32 + l;
+            key[it] = (i < n) ? kin[i] : (K)0;
+            if (VOUT) val[it] = (i < n) ? vgen(i) : 0u;
+        }
+    }
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
         u32 i = base + it * 32 + l;
@@ -262,16 +267,28 @@ rs_onesweep_kernel(const K* __restrict__ kin, ValGen vgen, const u32* __restrict
         rs_st_desc(mine, real | (tile == 0 ? kRsFlagInc : kRsFlagAgg));
         u32 before = 0;   // records with this digit in the tiles before this one
         if (tile > 0) {
-            const u32* p = mine;
-            for (u32 t = tile; t > 0; t--) {
-                p -= 256;
-                u32 v;
-                do {
-                    v = rs_ld_desc(p);
-                    BZ_SPIN_HINT();
-                } while ((v >> 30) == 0u);
-                before += v & kRsValMask;
-                if (v & kRsFlagInc) break;
+            // decoupled look-back, eight predecessors per round trip: their descriptors are requested together, then
+            // consumed nearest first (a descriptor that is not there yet is polled; an inclusive prefix ends the walk)
+            constexpr int LB = 8;
+            s32 t = (s32)tile - 1;
+            bool done = false;
+            while (!done) {
+                u32 v[LB];
+#pragma unroll
+                for (int k = 0; k < LB; k++) v[k] = (t - k >= 0) ? rs_ld_desc(desc + (size_t)(t - k) * 256 + d) : kRsFlagInc;
+#pragma unroll
+                for (int k = 0; k < LB; k++) {
+                    if (!done) {
+                        u32 x = v[k];
+                        while ((x >> 30) == 0u) {
+                            BZ_SPIN_HINT();
+                            x = rs_ld_desc(desc + (size_t)(t - k) * 256 + d);
+                        }
+                        before += x & kRsValMask;
+                        done = (x & kRsFlagInc) != 0u;
+                    }
+                }
+                t -= LB;
             }
             rs_st_desc(mine, (before + real) | kRsFlagInc);
         }
@@ -343,9 +360,11 @@ template <typename K>
 cudaError_t rs_histograms(cudaStream_t st, const K* keys, u32 n, int nbits, const RsTemp<K>& T) {
     const int npass = (nbits + 7) / 8;
     BZ_CUDA_TRY(cudaMemsetAsync(T.ghist, 0, sizeof(u32) * 256 * kRsMaxPasses, st));
-    const u32 chunks = (n + kRsThreads * 8 - 1) / (kRsThreads * 8);
-    const u32 grid = chunks < 148u * 8u ? chunks : 148u * 8u;
-    BZ_LAUNCH(grid, kRsThreads, 0, st, rs_hist_all_kernel<K>)(keys, n, nbits, T.ghist); BZ_NOTE_LAUNCH();
+    const u32 chunks = (n + kRsThreads * kRsHistItems - 1) / (kRsThreads * kRsHistItems);
+    const u32 grid = chunks < 148u * 3u ? chunks : 148u * 3u;   // persistent: 3 blocks per SM (64 KiB of counters each)
+    const size_t smem = rs_hist_smem(npass);
+    BZ_CUDA_TRY(cudaFuncSetAttribute(rs_hist_all_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BZ_LAUNCH(grid, kRsThreads, smem, st, rs_hist_all_kernel<K>)(keys, n, nbits, T.ghist); BZ_NOTE_LAUNCH();
     BZ_LAUNCH(1, 32 * kRsMaxPasses, 0, st, rs_digit_scan_kernel)(T.ghist, npass); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
     return cudaSuccess;
@@ -359,7 +378,8 @@ cudaError_t rs_pass_sweep(cudaStream_t st, const K* kin, ValGen vgen, const u32*
     const u32 mask = (1u << bits) - 1u;
     BZ_CUDA_TRY(cudaMemsetAsync(T.desc, 0, sizeof(u32) * 256 * (size_t)ntiles, st));
     BZ_CUDA_TRY(cudaMemsetAsync(T.ticket, 0, sizeof(u32), st));
-    auto kern = rs_onesweep_kernel<K, KOUT, VOUT, VTMA, ValGen>;
+    static const bool use_tma = !(getenv("BZ3_B200_RS_TMA") && getenv("BZ3_B200_RS_TMA")[0] == '0');   // A/B switch (tuning)
+    auto kern = use_tma ? rs_onesweep_kernel<K, KOUT, VOUT, VTMA, true, ValGen> : rs_onesweep_kernel<K, KOUT, VOUT, VTMA, false, ValGen>;
     const size_t smem = rs_scatter_smem<K>();
     // set every time: the attribute is per device and a process may drive several GPUs
     BZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -124,7 +124,7 @@ EXPORT int32_t emu_stage_lzp_encode(const uint8_t* in, int32_t n, uint8_t* out) 
     for (int i = 0; i < 2; i++) B.idx[i] = P.take<u32>(m);
     B.P = P.take<u32>((size_t)n + 8);
     B.code = P.take<u8>((size_t)n + 8);
-    B.skipbits = P.take<u32>((size_t)(n + 31) / 32 + 1);
+    B.lut = P.take<s32>((size_t)kLzpSlots);
     B.temp = P.take<u32>(rs_temp_elems<u32>(m));
     u8* src = P.take<u8>((size_t)n + 64);
     memcpy(src, in, (size_t)n);
