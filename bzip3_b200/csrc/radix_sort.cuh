@@ -250,7 +250,8 @@ rs_onesweep_kernel(const K* __restrict__ kin, ValGen vgen, const u32* __restrict
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive scan over warps, the tile's count -> descriptor, look-back, exclusive scan over digits
+    // per digit: exclusive scan over warps, the tile's count -> descriptor ("tile total"), exclusive scan over digits
+    u32 my_real;
     {
         const u32 d = threadIdx.x;
         u32 s = 0;
@@ -263,12 +264,39 @@ rs_onesweep_kernel(const K* __restrict__ kin, ValGen vgen, const u32* __restrict
         // digit 255 also holds the padding records of a partial tile; exclude them from the real count
         u32 real = s;
         if (d == 255) real -= (TILE - count);
+        my_real = real;
+        rs_st_desc(desc + (size_t)tile * 256 + d, real | (tile == 0 ? kRsFlagInc : kRsFlagAgg));
+        u32 incl = warp_scan_incl(real);
+        __shared__ u32 wsum[kRsWarps];
+        if (l == 31) wsum[w] = incl;
+        __syncthreads();
+        u32 wp = 0;
+#pragma unroll
+        for (int k = 0; k < kRsWarps; k++)
+            if ((u32)k < w) wp += wsum[k];
+        lbase[d] = wp + incl - real;
+    }
+    __syncthreads();
+    // the tile goes to shared memory in sorted order (local offsets only) ...
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        u32 i = base + it * 32 + l;
+        u32 d = (i < n) ? rs_digit(key[it], shift, mask) : 255u;
+        u32 pos = lbase[d] + warp_cnt[w * 256 + d] + rank[it];
+        if (pos < TILE) {
+            if (KOUT) skeys[pos] = key[it];
+            if (VOUT) svals[pos] = val[it];
+            if (!KOUT) reinterpret_cast<u8*>(skeys)[pos] = (u8)d;  // digit is still needed for the write-out
+        }
+    }
+    // ... while the tiles before this one finish counting: decoupled look-back, eight predecessors per round trip (their
+    // descriptors are requested together, then consumed nearest first; a descriptor that is not there yet is polled; an
+    // inclusive prefix ends the walk)
+    {
+        const u32 d = threadIdx.x;
         u32* mine = desc + (size_t)tile * 256 + d;
-        rs_st_desc(mine, real | (tile == 0 ? kRsFlagInc : kRsFlagAgg));
         u32 before = 0;   // records with this digit in the tiles before this one
         if (tile > 0) {
-            // decoupled look-back, eight predecessors per round trip: their descriptors are requested together, then
-            // consumed nearest first (a descriptor that is not there yet is polled; an inclusive prefix ends the walk)
             constexpr int LB = 8;
             s32 t = (s32)tile - 1;
             bool done = false;
@@ -290,31 +318,9 @@ rs_onesweep_kernel(const K* __restrict__ kin, ValGen vgen, const u32* __restrict
                 }
                 t -= LB;
             }
-            rs_st_desc(mine, (before + real) | kRsFlagInc);
+            rs_st_desc(mine, (before + my_real) | kRsFlagInc);
         }
-        u32 incl = warp_scan_incl(real);
-        __shared__ u32 wsum[kRsWarps];
-        if (l == 31) wsum[w] = incl;
-        __syncthreads();
-        u32 wp = 0;
-#pragma unroll
-        for (int k = 0; k < kRsWarps; k++)
-            if ((u32)k < w) wp += wsum[k];
-        u32 excl = wp + incl - real;
-        lbase[d] = excl;
-        gdelta[d] = gbase[d] + before - excl;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < ITEMS; it++) {
-        u32 i = base + it * 32 + l;
-        u32 d = (i < n) ? rs_digit(key[it], shift, mask) : 255u;
-        u32 pos = lbase[d] + warp_cnt[w * 256 + d] + rank[it];
-        if (pos < TILE) {
-            if (KOUT) skeys[pos] = key[it];
-            if (VOUT) svals[pos] = val[it];
-            if (!KOUT) reinterpret_cast<u8*>(skeys)[pos] = (u8)d;  // digit is still needed for the write-out
-        }
+        gdelta[d] = gbase[d] + before - lbase[d];
     }
     __syncthreads();
     for (u32 j = threadIdx.x; j < count; j += kRsThreads) {
