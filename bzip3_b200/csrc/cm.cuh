@@ -203,80 +203,17 @@ BZ_D u32 mulhi_pinned(u32 a, u32 b) {
 }
 
 // ---- range coder lane -------------------------------------------------------------------------
-// Measured on B200 (profiles/r01_ncu_source_cm_*): for one in-order thread a TAKEN branch costs ~28
-// cycles and every dependent ALU instruction ~4-5, so the byte is coded in two tiers:
-//   fast tier   eight decisions with no branch at all.  No renormalisation is applied; instead the
-//               minimum over the eight steps of  low ^ (low + range)  is kept.  If it never dropped below
-//               2^24 no byte had to be shifted out and the result is exact.
-//   exact tier  otherwise the byte is redone from its saved start state with the reference loop.
-// For BWT output most bytes take the fast tier (a byte is shifted out every ~40 decisions).
-// Recurrence in (low, range) form:  x = umulhi(range, P << 14)  ( == (range * P) >> 18 ),
-//     bit 1: range = x            bit 0: low += x + 1, range -= x + 1
-BZ_D void rc_fast_step(u32& low, u32& range, u32& x, u32& tmin, u32 bit, u32 mnext) {
-#if defined(BZ_EMU)
-    if (bit) range = x; else { low += x + 1u; range -= x + 1u; }
-    x = __umulhi(range, mnext);
-    const u32 t = low ^ (low + range);
-    tmin = t < tmin ? t : tmin;
-#else
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pb;\n\t"
-        ".reg .u32 hi, t, r0;\n\t"
-        "setp.ne.u32 pb, %4, 0;\n\t"
-        "sub.u32 r0, %1, %2;\n\t"          // range - x - 1 (one 3-input add)
-        "add.u32 r0, r0, -1;\n\t"
-        "selp.u32 %1, %2, r0, pb;\n\t"     // bit 1: range = x    bit 0: range -= x + 1
-        "mul.hi.u32 r0, %1, %5;\n\t"       // product for the next decision
-        "@!pb add.u32 %0, %0, %2;\n\t"     // bit 0: low += x + 1
-        "@!pb add.u32 %0, %0, 1;\n\t"
-        "mov.u32 %2, r0;\n\t"
-        "add.u32 hi, %0, %1;\n\t"
-        "xor.b32 t, %0, hi;\n\t"
-        "min.u32 %3, %3, t;\n\t"
-        "}"
-        : "+r"(low), "+r"(range), "+r"(x), "+r"(tmin)
-        : "r"(bit), "r"(mnext));
-#endif
-}
-
-// exact tier, one decision: same recurrence, then the renormalisation of the reference.  range < 2^24 is
-// necessary for the top bytes of low and low+range to agree, so that cheap test guards the loop.
-BZ_D void rc_exact_step(u32& low, u32& range, u32& x, s32& op, u32 bit, u32 mnext, u8* __restrict__ out) {
-    u32 slow;
-#if defined(BZ_EMU)
-    if (bit) range = x; else { low += x + 1u; range -= x + 1u; }
-    x = __umulhi(range, mnext);
-    slow = range < 0x1000000u;
-#else
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pb, ps;\n\t"
-        ".reg .u32 nx;\n\t"
-        "setp.ne.u32 pb, %4, 0;\n\t"
-        "not.b32 nx, %2;\n\t"
-        "@pb mov.u32 %1, %2;\n\t"
-        "@!pb add.u32 %1, %1, nx;\n\t"
-        "mul.hi.u32 %2, %1, %5;\n\t"
-        "@!pb sub.u32 %0, %0, nx;\n\t"
-        "setp.lt.u32 ps, %1, 0x1000000;\n\t"
-        "selp.u32 %3, 1, 0, ps;\n\t"
-        "}"
-        : "+r"(low), "+r"(range), "+r"(x), "=r"(slow)
-        : "r"(bit), "r"(mnext));
-#endif
-    if (slow) {
-        u32 high = low + range;
-        while ((low ^ high) < (1u << 24)) {
-            out[op++] = (u8)(low >> 24);
-            low <<= 8;
-            high = (high << 8) | 0xFFu;
-        }
-        range = high - low;
-        x = mulhi_pinned(range, mnext);
-    }
-}
-
+// Measured on B200 (profiles/r01_ncu_source_cm_*, r02_call3_ubench_walk.log): one in-order thread pays ~2.5-5 cycles per
+// dependent instruction and ~25-50 per conditional branch, taken or not, so a byte is coded in two tiers:
+//   fast tier   eight decisions with no branch at all and ONE multiply each: with m = bit ? M : -M (M = P << 14) the new
+//               range is hi32(range * m) -- for a 1-bit that is x = (range * P) >> 18, for a 0-bit range - x - 1 unless
+//               lo32(range * M) == 0.  low moves by the range lost at 0-bits.  No shift is applied; the minimum over the
+//               eight decisions of low ^ (low + range) tells whether one was due (most bytes of BWT output: none).
+//   exact tier  otherwise the byte is redone from its start state, still without a branch: one PREDICATED one-byte shift
+//               per decision; only a decision that needs a second shift (probability < 2^-8) falls back to the
+//               reference's loop (src/libbz3.c:388-416).
+// Measured steps (profiles/r02_call16_*, r02_call17_*): one multiply instead of multiply + select chain -3 %, predicated
+// exact byte instead of a loop with a branch per decision -11 % (Zipf) / -8 % (source).
 // Three-stage chunk pipeline (one __syncthreads per chunk, no polling):
 //   warp 0, lanes 0..7  stage 1: c0 / c1 counters of tree depth `lane`  -> mixed probability p (16 bit)
 //   warp 2, lanes 0..7  stage 2: SSE rows c2 of depth `lane`            -> P << 14
@@ -350,7 +287,10 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_kernel(const u8* __re
                     u16* cell = c2 + (2 * node + flag) * 17 + (p >> 12);
                     const int lo = cell[0], hi = cell[1];
                     const int sse = lo + (((hi - lo) * (p & 4095)) >> 12);
-                    pb[k * 8] = (u32)(sse * 3 + p) << 14;
+                    {
+                        const u32 m = (u32)(sse * 3 + p) << 14;
+                        pb[k * 8] = ones ? m : 0u - m;   // the coder lane multiplies by M for a 1-bit and by -M for a 0-bit
+                    }
                     cell[0] = (u16)cm_adapt_bf((u32)lo, ones, 6);
                     cell[1] = (u16)cm_adapt_bf((u32)hi, ones, 6);
                     prev2 = prev1;
@@ -367,7 +307,6 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_kernel(const u8* __re
                 const u8* sb = sbytes + (ch % 3) * kCmEncChunk;
                 uint4 a = pv[0], b = pv[1];
                 u32 sym = sb[0];
-                u32 x = mulhi_pinned(range, a.x);
                 for (s32 k = 0; k < len; k++) {
                     const uint4 ca = a, cb = b;
                     const u32 cs = sym;
@@ -385,28 +324,71 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_kernel(const u8* __re
                         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym) : "r"(sp));
 #endif
                     }
-                    const u32 low0 = low, range0 = range, x0 = x;
-                    u32 tmin = 0xFFFFFFFFu;
-                    rc_fast_step(low, range, x, tmin, cs & 0x80u, ca.y);
-                    rc_fast_step(low, range, x, tmin, cs & 0x40u, ca.z);
-                    rc_fast_step(low, range, x, tmin, cs & 0x20u, ca.w);
-                    rc_fast_step(low, range, x, tmin, cs & 0x10u, cb.x);
-                    rc_fast_step(low, range, x, tmin, cs & 0x08u, cb.y);
-                    rc_fast_step(low, range, x, tmin, cs & 0x04u, cb.z);
-                    rc_fast_step(low, range, x, tmin, cs & 0x02u, cb.w);
-                    rc_fast_step(low, range, x, tmin, cs & 0x01u, a.x);
-                    if (tmin < (1u << 24)) {  // some decision needed a shift: redo this byte exactly
-                        low = low0;
-                        range = range0;
-                        x = x0;
-                        rc_exact_step(low, range, x, op, cs & 0x80u, ca.y, out);
-                        rc_exact_step(low, range, x, op, cs & 0x40u, ca.z, out);
-                        rc_exact_step(low, range, x, op, cs & 0x20u, ca.w, out);
-                        rc_exact_step(low, range, x, op, cs & 0x10u, cb.x, out);
-                        rc_exact_step(low, range, x, op, cs & 0x08u, cb.y, out);
-                        rc_exact_step(low, range, x, op, cs & 0x04u, cb.z, out);
-                        rc_exact_step(low, range, x, op, cs & 0x02u, cb.w, out);
-                        rc_exact_step(low, range, x, op, cs & 0x01u, a.x, out);
+                    {
+                        // one multiply per decision: bit 1: new range = hi32(range * M) = x; bit 0: range - x - 1 = hi32(range * -M)
+                        // unless lo32(range * M) == 0 (range * (2^32 - M) = range * 2^32 - range * M).  low moves by the range
+                        // lost at 0-bits.  No shift is applied; the minimum of low ^ (low + range) over the eight decisions tells
+                        // whether one was due, the minimum of the low halves whether the shortcut was exact.
+                        const u32 m[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                        u32 l = low, r = range, tmin = 0xFFFFFFFFu, zmin = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const u64 w = (u64)r * (u64)m[j];
+                            const u32 rn = (u32)(w >> 32);
+                            zmin = min(zmin, (u32)w);
+                            if (!(cs & (0x80u >> j))) l += r - rn;
+                            r = rn;
+                            tmin = min(tmin, l ^ (l + r));
+                        }
+                        if (tmin >= (1u << 24) && zmin != 0u) {
+                            low = l;
+                            range = r;
+                        } else {
+                            // A shift was due somewhere in this byte: redo it exactly -- branch-free, one predicated one-byte
+                            // shift per decision (the common case: a decision shifts at most one byte out); only a decision
+                            // that needs a second shift sends the byte to the reference's loop below.
+                            bool done = false;
+                            {
+                                u32 lo2 = low, rg = range;
+                                s32 o2 = op;
+                                bool multi = false;
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    const bool bit = (cs & (0x80u >> j)) != 0;
+                                    const u32 xx = __umulhi(rg, bit ? m[j] : 0u - m[j]);
+                                    rg = bit ? xx : rg - xx - 1u;
+                                    lo2 = bit ? lo2 : lo2 + xx + 1u;
+                                    const bool sh = ((lo2 ^ (lo2 + rg)) < (1u << 24));
+                                    if (sh) out[o2] = (u8)(lo2 >> 24);
+                                    o2 += sh ? 1 : 0;
+                                    lo2 = sh ? lo2 << 8 : lo2;
+                                    rg = sh ? (rg << 8) | 0xFFu : rg;
+                                    multi = multi || (sh && ((lo2 ^ (lo2 + rg)) < (1u << 24)));
+                                }
+                                if (!multi) {
+                                    low = lo2;
+                                    range = rg;
+                                    op = o2;
+                                    done = true;
+                                }
+                            }
+                            if (!done) {   // the reference's loop (src/libbz3.c:388-416)
+                                u32 lo2 = low, high = low + range;
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    const bool bit = (cs & (0x80u >> j)) != 0;
+                                    const u32 xx = __umulhi(high - lo2, bit ? m[j] : 0u - m[j]);
+                                    if (bit) high = lo2 + xx; else lo2 += xx + 1u;
+                                    while ((lo2 ^ high) < (1u << 24)) {
+                                        out[op++] = (u8)(lo2 >> 24);
+                                        lo2 <<= 8;
+                                        high = (high << 8) | 0xFFu;
+                                    }
+                                }
+                                low = lo2;
+                                range = high - lo2;
+                            }
+                        }
                     }
                 }
             }
