@@ -189,6 +189,18 @@ constexpr int kCmEncChunk = 768;
 constexpr int kCmEncThreads = 96;
 constexpr size_t kCmEncSmemBytes = (size_t)kCmTableU16 * 2 + 2 * (size_t)kCmEncChunk * 8 * 4 + 2 * (size_t)kCmEncChunk * 8 * 2 + 3 * (size_t)kCmEncChunk + 64;
 
+// 32 x 32 -> 64 bit product as two registers (one IMAD.WIDE; no 64-bit shift for the compiler to lower into an extra add on
+// the chain: -5 % (Zipf) / -8 % (source) encode time, profiles/r02_call17_cm_encoder_branch_free_exact_byte.log)
+BZ_D void cm_mul_wide_halves(u32 a, u32 b, u32& lo, u32& hi) {
+#if defined(BZ_EMU)
+    const u64 w = (u64)a * (u64)b;
+    lo = (u32)w;
+    hi = (u32)(w >> 32);
+#else
+    asm("{\n\t.reg .u64 w;\n\tmul.wide.u32 w, %2, %3;\n\tmov.b64 {%0, %1}, w;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#endif
+}
+
 // mul.hi that the compiler may neither sink into a branch nor drop: it is issued speculatively for the
 // NEXT decision before the (rare) renormalisation test of the current one has resolved, which takes the
 // test off the critical recurrence  range -> mul.hi -> range.
@@ -333,9 +345,9 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_kernel(const u8* __re
                         u32 l = low, r = range, tmin = 0xFFFFFFFFu, zmin = 0xFFFFFFFFu;
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            const u64 w = (u64)r * (u64)m[j];
-                            const u32 rn = (u32)(w >> 32);
-                            zmin = min(zmin, (u32)w);
+                            u32 rn, wl;
+                            cm_mul_wide_halves(r, m[j], wl, rn);
+                            zmin = min(zmin, wl);
                             if (!(cs & (0x80u >> j))) l += r - rn;
                             r = rn;
                             tmin = min(tmin, l ^ (l + r));
