@@ -219,13 +219,99 @@ BZ_D u32 mulhi_pinned(u32 a, u32 b) {
 // dependent instruction and ~25-50 per conditional branch, taken or not, so a byte is coded in two tiers:
 //   fast tier   eight decisions with no branch at all and ONE multiply each: with m = bit ? M : -M (M = P << 14) the new
 //               range is hi32(range * m) -- for a 1-bit that is x = (range * P) >> 18, for a 0-bit range - x - 1 unless
-//               lo32(range * M) == 0.  low moves by the range lost at 0-bits.  No shift is applied; the minimum over the
-//               eight decisions of low ^ (low + range) tells whether one was due (most bytes of BWT output: none).
+//               lo32(range * M) == 0.  low moves by the range lost at 0-bits.  No shift is applied; the intervals are
+//               nested, so low ^ (low + range) after the eighth decision tells whether one was due anywhere in the byte
+//               (most bytes of BWT output: none).
 //   exact tier  otherwise the byte is redone from its start state, still without a branch: one PREDICATED one-byte shift
 //               per decision; only a decision that needs a second shift (probability < 2^-8) falls back to the
 //               reference's loop (src/libbz3.c:388-416).
 // Measured steps (profiles/r02_call16_*, r02_call17_*): one multiply instead of multiply + select chain -3 %, predicated
 // exact byte instead of a loop with a branch per decision -11 % (Zipf) / -8 % (source).
+
+// entries (m = bit ? M : -M, eight per byte) and the byte itself of position k of the chunk: pinned loads, issued where written
+BZ_D void cm_enc_fetch(const uint4* pv, const u8* sb, s32 k, uint4& a, uint4& b, u32& sym) {
+#if defined(BZ_EMU)
+    a = pv[2 * k];
+    b = pv[2 * k + 1];
+    sym = sb[k];
+#else
+    const u32 ap = (u32)__cvta_generic_to_shared(pv + 2 * k);
+    const u32 sp = (u32)__cvta_generic_to_shared(sb + k);
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(ap));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(ap));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym) : "r"(sp));
+#endif
+}
+
+// One byte through the range coder lane (tiers: see above).
+BZ_D void cm_code_byte(const uint4 ca, const uint4 cb, const u32 cs, u32& low, u32& range, s32& op, u8* __restrict__ out) {
+    // one multiply per decision: bit 1: new range = hi32(range * M) = x; bit 0: range - x - 1 = hi32(range * -M)
+    // unless lo32(range * M) == 0 (range * (2^32 - M) = range * 2^32 - range * M).  low moves by the range
+    // lost at 0-bits.  No shift is applied; the minimum of the low halves tells whether the shortcut was exact.
+    const u32 m[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+    u32 l = low, r = range, zmin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        u32 rn, wl;
+        cm_mul_wide_halves(r, m[j], wl, rn);
+        zmin = min(zmin, wl);
+        if (!(cs & (0x80u >> j))) l += r - rn;
+        r = rn;
+    }
+    // The intervals are nested and no shift was applied, so once the top bytes of low and low + range agree they agree
+    // for the rest of the byte: ONE test after the eighth decision tells whether a shift was due anywhere in the byte
+    // (three instructions per decision less than a running minimum).
+    if (((l ^ (l + r)) >= (1u << 24)) && zmin != 0u) {
+        low = l;
+        range = r;
+        return;
+    }
+    // A shift was due somewhere in this byte: redo it exactly -- branch-free, one predicated one-byte shift per decision
+    // (the common case: a decision shifts at most one byte out); only a decision that needs a second shift sends the
+    // byte to the reference's loop below.
+    {
+        u32 lo2 = low, rg = range;
+        s32 o2 = op;
+        bool multi = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const bool bit = (cs & (0x80u >> j)) != 0;
+            const u32 xx = __umulhi(rg, bit ? m[j] : 0u - m[j]);
+            rg = bit ? xx : rg - xx - 1u;
+            lo2 = bit ? lo2 : lo2 + xx + 1u;
+            const bool sh = ((lo2 ^ (lo2 + rg)) < (1u << 24));
+            if (sh) out[o2] = (u8)(lo2 >> 24);
+            o2 += sh ? 1 : 0;
+            lo2 = sh ? lo2 << 8 : lo2;
+            rg = sh ? (rg << 8) | 0xFFu : rg;
+            multi = multi || (sh && ((lo2 ^ (lo2 + rg)) < (1u << 24)));
+        }
+        if (!multi) {
+            low = lo2;
+            range = rg;
+            op = o2;
+            return;
+        }
+    }
+    {   // the reference's loop (src/libbz3.c:388-416)
+        u32 lo2 = low, high = low + range;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const bool bit = (cs & (0x80u >> j)) != 0;
+            const u32 xx = __umulhi(high - lo2, bit ? m[j] : 0u - m[j]);
+            if (bit) high = lo2 + xx; else lo2 += xx + 1u;
+            while ((lo2 ^ high) < (1u << 24)) {
+                out[op++] = (u8)(lo2 >> 24);
+                lo2 <<= 8;
+                high = (high << 8) | 0xFFu;
+            }
+        }
+        low = lo2;
+        range = high - lo2;
+    }
+}
+
+
 // Three-stage chunk pipeline (one __syncthreads per chunk, no polling):
 //   warp 0, lanes 0..7  stage 1: c0 / c1 counters of tree depth `lane`  -> mixed probability p (16 bit)
 //   warp 2, lanes 0..7  stage 2: SSE rows c2 of depth `lane`            -> P << 14
@@ -317,91 +403,18 @@ __global__ void __launch_bounds__(kCmEncThreads) cm_encode_kernel(const u8* __re
                 const u32* pw = pbuf + (ch & 1) * (kCmEncChunk * 8);
                 const uint4* pv = reinterpret_cast<const uint4*>(pw);
                 const u8* sb = sbytes + (ch % 3) * kCmEncChunk;
-                uint4 a = pv[0], b = pv[1];
-                u32 sym = sb[0];
-                for (s32 k = 0; k < len; k++) {
-                    const uint4 ca = a, cb = b;
-                    const u32 cs = sym;
-                    const s32 kn = (k + 1 < len) ? k + 1 : k;  // the last byte re-reads itself; that product is unused
-                    {   // pinned prefetch of the next byte's entries: issued before this byte's decisions, not after
-#if defined(BZ_EMU)
-                        a = pv[2 * kn];
-                        b = pv[2 * kn + 1];
-                        sym = sb[kn];
-#else
-                        const u32 ap = (u32)__cvta_generic_to_shared(pv + 2 * kn);
-                        const u32 sp = (u32)__cvta_generic_to_shared(sb + kn);
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(ap));
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(ap));
-                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sym) : "r"(sp));
-#endif
-                    }
-                    {
-                        // one multiply per decision: bit 1: new range = hi32(range * M) = x; bit 0: range - x - 1 = hi32(range * -M)
-                        // unless lo32(range * M) == 0 (range * (2^32 - M) = range * 2^32 - range * M).  low moves by the range
-                        // lost at 0-bits.  No shift is applied; the minimum of low ^ (low + range) over the eight decisions tells
-                        // whether one was due, the minimum of the low halves whether the shortcut was exact.
-                        const u32 m[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                        u32 l = low, r = range, tmin = 0xFFFFFFFFu, zmin = 0xFFFFFFFFu;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            u32 rn, wl;
-                            cm_mul_wide_halves(r, m[j], wl, rn);
-                            zmin = min(zmin, wl);
-                            if (!(cs & (0x80u >> j))) l += r - rn;
-                            r = rn;
-                            tmin = min(tmin, l ^ (l + r));
-                        }
-                        if (tmin >= (1u << 24) && zmin != 0u) {
-                            low = l;
-                            range = r;
-                        } else {
-                            // A shift was due somewhere in this byte: redo it exactly -- branch-free, one predicated one-byte
-                            // shift per decision (the common case: a decision shifts at most one byte out); only a decision
-                            // that needs a second shift sends the byte to the reference's loop below.
-                            bool done = false;
-                            {
-                                u32 lo2 = low, rg = range;
-                                s32 o2 = op;
-                                bool multi = false;
-#pragma unroll
-                                for (int j = 0; j < 8; j++) {
-                                    const bool bit = (cs & (0x80u >> j)) != 0;
-                                    const u32 xx = __umulhi(rg, bit ? m[j] : 0u - m[j]);
-                                    rg = bit ? xx : rg - xx - 1u;
-                                    lo2 = bit ? lo2 : lo2 + xx + 1u;
-                                    const bool sh = ((lo2 ^ (lo2 + rg)) < (1u << 24));
-                                    if (sh) out[o2] = (u8)(lo2 >> 24);
-                                    o2 += sh ? 1 : 0;
-                                    lo2 = sh ? lo2 << 8 : lo2;
-                                    rg = sh ? (rg << 8) | 0xFFu : rg;
-                                    multi = multi || (sh && ((lo2 ^ (lo2 + rg)) < (1u << 24)));
-                                }
-                                if (!multi) {
-                                    low = lo2;
-                                    range = rg;
-                                    op = o2;
-                                    done = true;
-                                }
-                            }
-                            if (!done) {   // the reference's loop (src/libbz3.c:388-416)
-                                u32 lo2 = low, high = low + range;
-#pragma unroll
-                                for (int j = 0; j < 8; j++) {
-                                    const bool bit = (cs & (0x80u >> j)) != 0;
-                                    const u32 xx = __umulhi(high - lo2, bit ? m[j] : 0u - m[j]);
-                                    if (bit) high = lo2 + xx; else lo2 += xx + 1u;
-                                    while ((lo2 ^ high) < (1u << 24)) {
-                                        out[op++] = (u8)(lo2 >> 24);
-                                        lo2 <<= 8;
-                                        high = (high << 8) | 0xFFu;
-                                    }
-                                }
-                                low = lo2;
-                                range = high - lo2;
-                            }
-                        }
-                    }
+                // Two bytes per trip with two register sets: the entries of byte k + 1 are requested before byte k is coded and
+                // nothing has to be copied from "next" to "current" at the back edge (eight moves per byte in a one-byte loop).
+                uint4 a0 = pv[0], b0 = pv[1], a1, b1;
+                u32 sym0 = sb[0], sym1;
+                for (s32 k = 0; k < len; k += 2) {
+                    const s32 k1 = (k + 1 < len) ? k + 1 : k;   // past the end: re-read the last byte, the values are unused
+                    cm_enc_fetch(pv, sb, k1, a1, b1, sym1);
+                    cm_code_byte(a0, b0, sym0, low, range, op, out);
+                    if (k + 1 >= len) break;
+                    const s32 k2 = (k + 2 < len) ? k + 2 : k + 1;
+                    cm_enc_fetch(pv, sb, k2, a0, b0, sym0);
+                    cm_code_byte(a1, b1, sym1, low, range, op, out);
                 }
             }
         }
@@ -480,7 +493,7 @@ BZ_D void cm_model_predict(CmModelState& M, u32* ptab, u16* rows, const int node
 }
 
 template <int HALF>
-BZ_D void cm_model_step(CmModelState& M, u16* cm_smem, u32* ptab, volatile u32* vbyte, const bool last, const int node,
+BZ_D void cm_model_step(CmModelState& M, u16* cm_smem, u32* ptab, volatile u32* vbyte, const int node,
                         const int sh, u16* q0, u16* c1col, u16* rows) {
     // speculation: this byte == prev1
     const u32 hyp = (u32)M.prev1;
@@ -510,27 +523,22 @@ BZ_D void cm_model_step(CmModelState& M, u16* cm_smem, u32* ptab, volatile u32* 
     __syncthreads();   // byte ready
     const u32 byte = vbyte[HALF];
     if (__builtin_expect(byte != hyp, 0)) {   // uniform across the CTA
-        // miss: learn the byte that really came, then predict the next one for real
-        u32 na = M.a, nb = M.b;
-        if (node != 0 && ((256u | byte) >> sh) == (u32)node) {
-            const u32 ones = ((byte >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
-            na = cm_adapt_bf(M.a, ones, 2);
-            nb = cm_adapt_bf(M.b, ones, 4);
-            *q0 = (u16)na;
-            *M.q1 = (u16)nb;
-            M.cell[0] = (u16)cm_adapt_bf(M.lo, ones, 6);
-            M.cell[1] = (u16)cm_adapt_bf(M.hi, ones, 6);
-        }
+        // miss: learn the byte that really came, then predict the next one for real.  No further branch on this path (the
+        // chain warp is waiting for it): the learn step is predicated, and the prediction after the last byte of the block is
+        // simply made and never used (the chain warp takes the matching barrier after its loop).
+        const bool on_b = node != 0 && ((256u | byte) >> sh) == (u32)node;
+        const u32 ones = ((byte >> (sh - 1)) & 1u) ? 0xFFFFu : 0u;
+        const u32 na = on_b ? cm_adapt_bf(M.a, ones, 2) : M.a;
+        const u32 nb = on_b ? cm_adapt_bf(M.b, ones, 4) : M.b;
+        cm_learn_stores(on_b, q0, na, M.q1, nb, M.cell, cm_adapt_bf(M.lo, ones, 6), cm_adapt_bf(M.hi, ones, 6));
         M.a = na;
         M.d = nb;                       // this byte's order-1 counter is the next byte's prev2 counter
         M.prev2 = M.prev1;
         M.prev1 = (int)byte;
         M.q1 = c1col + M.prev1 * 256;
         M.b = *M.q1;                    // after the store above in program order
-        if (!last) {
-            cm_model_predict<HALF ^ 1>(M, ptab, rows, node);
-            __syncthreads();   // ptab ready
-        }
+        cm_model_predict<HALF ^ 1>(M, ptab, rows, node);
+        __syncthreads();   // ptab ready
         return;
     }
     cm_learn_stores(on_h, q0, a_s, M.q1, b_s, M.cell, nl, nh);
@@ -564,8 +572,8 @@ BZ_D void cm_dec_model_thread(u16* cm_smem, u32* ptab, volatile u32* vbyte, s32 
     cm_model_predict<0>(M, ptab, rows, node);
     __syncthreads();   // ptab of byte 0 ready
     for (s32 i = 0; i < n; i += 2) {
-        cm_model_step<0>(M, cm_smem, ptab, vbyte, i + 1 >= n, node, sh, q0, c1col, rows);
-        if (i + 1 < n) cm_model_step<1>(M, cm_smem, ptab, vbyte, i + 2 >= n, node, sh, q0, c1col, rows);
+        cm_model_step<0>(M, cm_smem, ptab, vbyte, node, sh, q0, c1col, rows);
+        if (i + 1 < n) cm_model_step<1>(M, cm_smem, ptab, vbyte, node, sh, q0, c1col, rows);
     }
 }
 
@@ -632,7 +640,6 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_kernel(const u8* __re
             u32 flow = low, frange = range;
             u32 pcur = g0.y, kid0 = g0.z, kid1 = g0.w;
             u32 x = mulhi_pinned(frange, pcur);
-            u32 tmin = 0xFFFFFFFFu;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 u32 bit;
@@ -644,28 +651,23 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_kernel(const u8* __re
                     pcur = bit ? kid1 : kid0;
                     x = __umulhi(frange, pcur);
                     if (!bit) flow = mid + 1u;
-                    const u32 t = flow ^ (flow + frange);
-                    tmin = t < tmin ? t : tmin;
                 }
 #else
                 asm volatile(
                     "{\n\t"
                     ".reg .pred pb;\n\t"
-                    ".reg .u32 mid, nx, r0, hi, t;\n\t"
+                    ".reg .u32 mid, nx, r0;\n\t"
                     "add.u32 mid, %0, %2;\n\t"
                     "not.b32 nx, %2;\n\t"
-                    "setp.le.u32 pb, %6, mid;\n\t"        // bit = code <= low + x
+                    "setp.le.u32 pb, %5, mid;\n\t"        // bit = code <= low + x
                     "add.u32 r0, %1, nx;\n\t"             // range - x - 1
                     "selp.u32 %1, %2, r0, pb;\n\t"        // bit ? x : range - x - 1
-                    "selp.u32 %3, %8, %7, pb;\n\t"        // P of the chosen child
+                    "selp.u32 %3, %7, %6, pb;\n\t"        // P of the chosen child
                     "mul.hi.u32 %2, %1, %3;\n\t"          // product for the next step
                     "@!pb add.u32 %0, mid, 1;\n\t"        // bit 0: low = mid + 1
                     "selp.u32 %4, 1, 0, pb;\n\t"
-                    "add.u32 hi, %0, %1;\n\t"
-                    "xor.b32 t, %0, hi;\n\t"
-                    "min.u32 %5, %5, t;\n\t"
                     "}"
-                    : "+r"(flow), "+r"(frange), "+r"(x), "+r"(pcur), "=r"(bit), "+r"(tmin)
+                    : "+r"(flow), "+r"(frange), "+r"(x), "+r"(pcur), "=r"(bit)
                     : "r"(code), "r"(kid0), "r"(kid1));
 #endif
                 node = node * 2 + bit;
@@ -674,68 +676,163 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_kernel(const u8* __re
                 if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
             }
             BZ_PROF(1);
-            if (tmin >= (1u << 24)) {
+            // The intervals of the eight steps are nested and nothing was shifted, so the top bytes of low and low + range,
+            // once equal, stay equal: one test after the byte tells whether a renormalisation was due at ANY step.  Nested
+            // needs low <= code <= high, which every decision preserves and only read_in() past the end of the payload
+            // (the int -1, src/libbz3.c:345, :473) can break: an exhausted stream decodes in the exact tier.
+            if (((flow ^ (flow + frange)) >= (1u << 24)) && ip < insize) {
                 low = flow;
                 range = frange;
             } else {
 #ifdef BZ_CM_PROFILE
                 _acc[4]++;
 #endif
-                // exact tier: same walk, renormalising after every step like the reference
-                node = 1;
-                gk = *reinterpret_cast<const uint4*>(pt + 4);
-                pcur = g0.y;
-                kid0 = g0.z;
-                kid1 = g0.w;
-                x = mulhi_pinned(range, pcur);
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    u32 bit, slow;
+                bool done = false;
+                // exact tier A: the same walk with ONE predicated one-byte renormalisation per step and no branch (a branch per
+                // step costs more than the step).  The next four payload bytes wait in a register; with t = low ^ high a step
+                // that shifts once needs a second shift iff t < 2^16 (the new low ^ high is (t << 8) | 0xFF): such a byte, or one
+                // that shifts more than four times, or one within four bytes of the end of the payload, goes to tier B.
+                if (ip + 4 <= insize) {
+                    u32 W;
 #if defined(BZ_EMU)
-                    {
-                        const u32 mid = low + x;
-                        bit = code <= mid;
-                        range = bit ? x : range - x - 1u;
-                        pcur = bit ? kid1 : kid0;
-                        x = __umulhi(range, pcur);
-                        if (!bit) low = mid + 1u;
-                        slow = range < 0x1000000u;
-                    }
+                    W = ((u32)scode[ip & 2047] << 24) | ((u32)scode[(ip + 1) & 2047] << 16) | ((u32)scode[(ip + 2) & 2047] << 8) |
+                        (u32)scode[(ip + 3) & 2047];
 #else
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred pb, ps;\n\t"
-                        ".reg .u32 mid, nx, r0;\n\t"
-                        "add.u32 mid, %0, %2;\n\t"
-                        "not.b32 nx, %2;\n\t"
-                        "setp.le.u32 pb, %6, mid;\n\t"
-                        "add.u32 r0, %1, nx;\n\t"
-                        "selp.u32 %1, %2, r0, pb;\n\t"
-                        "selp.u32 %3, %8, %7, pb;\n\t"
-                        "mul.hi.u32 %2, %1, %3;\n\t"
-                        "@!pb add.u32 %0, mid, 1;\n\t"
-                        "selp.u32 %4, 1, 0, pb;\n\t"
-                        "setp.lt.u32 ps, %1, 0x1000000;\n\t"
-                        "selp.u32 %5, 1, 0, ps;\n\t"
-                        "}"
-                        : "+r"(low), "+r"(range), "+r"(x), "+r"(pcur), "=r"(bit), "=r"(slow)
-                        : "r"(code), "r"(kid0), "r"(kid1));
+                    W = __byte_perm(*reinterpret_cast<const u32*>(scode + (ip & 2044)),
+                                    *reinterpret_cast<const u32*>(scode + ((ip + 4) & 2044)), 0x0123u + (u32)(ip & 3) * 0x1111u);
 #endif
-                    node = node * 2 + bit;
-                    kid0 = bit ? gk.z : gk.x;
-                    kid1 = bit ? gk.w : gk.y;
-                    if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
-                    if (slow) {
-                        u32 high = low + range;
-                        while ((low ^ high) < (1u << 24)) {
-                            low <<= 8;
-                            high = (high << 8) | 0xFFu;
-                            const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;
-                            ip += (ip < insize);
-                            code = (code << 8) + add;
+                    u32 plow = low, prange = range, pcode = code, nsh = 0, multi = 0, pnode = 1;
+                    uint4 pg = *reinterpret_cast<const uint4*>(pt + 4);
+                    u32 pp = g0.y, pk0 = g0.z, pk1 = g0.w;
+                    u32 px = mulhi_pinned(prange, pp);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        u32 bit;
+#if defined(BZ_EMU)
+                        {
+                            const u32 mid = plow + px;
+                            bit = pcode <= mid;
+                            prange = bit ? px : prange - px - 1u;
+                            pp = bit ? pk1 : pk0;
+                            if (!bit) plow = mid + 1u;
+                            const u32 t = plow ^ (plow + prange);
+                            if (t < (1u << 24)) {
+                                plow <<= 8;
+                                prange = (prange << 8) | 0xFFu;
+                                pcode = (pcode << 8) | (W >> 24);
+                                W <<= 8;
+                                nsh++;
+                                if (t < (1u << 16)) multi = 1;
+                            }
+                            px = __umulhi(prange, pp);
                         }
-                        range = high - low;
-                        x = mulhi_pinned(range, pcur);
+#else
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred pb, ps, pm;\n\t"
+                            ".reg .u32 mid, nx, r0, hi, t;\n\t"
+                            "add.u32 mid, %0, %2;\n\t"
+                            "not.b32 nx, %2;\n\t"
+                            "setp.le.u32 pb, %5, mid;\n\t"
+                            "add.u32 r0, %1, nx;\n\t"
+                            "selp.u32 %1, %2, r0, pb;\n\t"
+                            "selp.u32 %3, %10, %9, pb;\n\t"
+                            "@!pb add.u32 %0, mid, 1;\n\t"
+                            "selp.u32 %4, 1, 0, pb;\n\t"
+                            "add.u32 hi, %0, %1;\n\t"
+                            "xor.b32 t, %0, hi;\n\t"
+                            "setp.lt.u32 ps, t, 0x1000000;\n\t"
+                            "setp.lt.u32 pm, t, 0x10000;\n\t"
+                            "@ps shl.b32 %0, %0, 8;\n\t"
+                            "@ps mad.lo.u32 %1, %1, 256, 255;\n\t"          // (range << 8) | 0xFF
+                            "@ps shf.l.clamp.b32 %5, %6, %5, 8;\n\t"        // code = (code << 8) | next payload byte
+                            "@ps shl.b32 %6, %6, 8;\n\t"
+                            "@ps add.u32 %7, %7, 1;\n\t"
+                            "@pm mov.u32 %8, 1;\n\t"
+                            "mul.hi.u32 %2, %1, %3;\n\t"
+                            "}"
+                            : "+r"(plow), "+r"(prange), "+r"(px), "+r"(pp), "=r"(bit), "+r"(pcode), "+r"(W), "+r"(nsh), "+r"(multi)
+                            : "r"(pk0), "r"(pk1));
+#endif
+                        pnode = pnode * 2 + bit;
+                        pk0 = bit ? pg.z : pg.x;
+                        pk1 = bit ? pg.w : pg.y;
+                        if (k < 5) pg = *reinterpret_cast<const uint4*>(pt + 4 * pnode);
+                    }
+                    if (multi == 0 && nsh <= 4) {
+                        low = plow;
+                        range = prange;
+                        code = pcode;
+                        ip += (s32)nsh;
+                        node = pnode;
+                        done = true;
+                    }
+                }
+                if (!done) {
+                    // exact tier B (rare: a step that shifts twice, more than four shifts in the byte, the end of the payload):
+                    // same walk, renormalising after every step with the reference's loop (src/libbz3.c:464-474).
+                    // range < 2^24 is necessary for equal top bytes only while low <= high, i.e. until the payload is exhausted
+                    // (see above); from then on every step takes the reference's test itself.
+                    // (Kept unrolled although it is rare: with a rolled loop here ptxas allocates the fast tier's table rows to
+                    // the registers it has just read, the loads issue late and the fast tier loses 100 cycles per byte --
+                    // profiles/r02_call26_cm_tier_b_rolled_loses.log.)
+                    node = 1;
+                    gk = *reinterpret_cast<const uint4*>(pt + 4);
+                    pcur = g0.y;
+                    kid0 = g0.z;
+                    kid1 = g0.w;
+                    x = mulhi_pinned(range, pcur);
+                    u32 exhausted = ip >= insize;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        u32 bit, slow;
+#if defined(BZ_EMU)
+                        {
+                            const u32 mid = low + x;
+                            bit = code <= mid;
+                            range = bit ? x : range - x - 1u;
+                            pcur = bit ? kid1 : kid0;
+                            x = __umulhi(range, pcur);
+                            if (!bit) low = mid + 1u;
+                            slow = range < 0x1000000u;
+                        }
+#else
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred pb, ps;\n\t"
+                            ".reg .u32 mid, nx, r0;\n\t"
+                            "add.u32 mid, %0, %2;\n\t"
+                            "not.b32 nx, %2;\n\t"
+                            "setp.le.u32 pb, %6, mid;\n\t"
+                            "add.u32 r0, %1, nx;\n\t"
+                            "selp.u32 %1, %2, r0, pb;\n\t"
+                            "selp.u32 %3, %8, %7, pb;\n\t"
+                            "mul.hi.u32 %2, %1, %3;\n\t"
+                            "@!pb add.u32 %0, mid, 1;\n\t"
+                            "selp.u32 %4, 1, 0, pb;\n\t"
+                            "setp.lt.u32 ps, %1, 0x1000000;\n\t"
+                            "selp.u32 %5, 1, 0, ps;\n\t"
+                            "}"
+                            : "+r"(low), "+r"(range), "+r"(x), "+r"(pcur), "=r"(bit), "=r"(slow)
+                            : "r"(code), "r"(kid0), "r"(kid1));
+#endif
+                        node = node * 2 + bit;
+                        kid0 = bit ? gk.z : gk.x;
+                        kid1 = bit ? gk.w : gk.y;
+                        if (k < 5) gk = *reinterpret_cast<const uint4*>(pt + 4 * node);
+                        if (slow | exhausted) {
+                            u32 high = low + range;
+                            while ((low ^ high) < (1u << 24)) {
+                                low <<= 8;
+                                high = (high << 8) | 0xFFu;
+                                const u32 add = (ip < insize) ? (u32)scode[ip & 2047] : 0xFFFFFFFFu;
+                                ip += (ip < insize);
+                                code = (code << 8) + add;
+                            }
+                            range = high - low;
+                            x = mulhi_pinned(range, pcur);
+                            exhausted = ip >= insize;
+                        }
                     }
                 }
             }
@@ -759,6 +856,7 @@ __global__ void __launch_bounds__(kCmDecThreads) cm_decode_kernel(const u8* __re
         have = byte == prevb;
         prevb = byte;
     }
+    if (n > 0 && !have) __syncthreads();   // the model threads predicted once more after a last byte that missed
 #ifdef BZ_CM_PROFILE
     if (tid == 0)
         for (int k = 0; k < 5; k++) g_cm_prof[8 + k] = _acc[k];   // wait ptab, fast tier, exact tier, publish+wait byte, #redo

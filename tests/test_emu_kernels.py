@@ -100,6 +100,34 @@ def test_cm_decode_kernel(name, data):
             assert bytes(got[:n]) == bytes(data)
 
 
+def test_cm_decode_exhausted_streams():
+    """Once the payload is exhausted read_in() feeds -1 (src/libbz3.c:345) and low <= code <= high no longer holds; the
+    kernel's shortcuts (one renormalisation test per byte, range < 2^24 as the cheap pre-test) are switched off from
+    there on, so truncated and garbage payloads decode exactly like the reference -- for as long as the caller asks."""
+    E, O = emu(), refs.oracle()
+    rng = np.random.default_rng(31337)
+    data = CM_CASES[CM_IDS.index("bwt_zipf_12k")][1][:1500]
+    n = len(data)
+    enc = np.zeros(2 * n + 64, np.uint8)
+    r = O.orc_cm_encode(refs.ptr(data), n, refs.ptr(enc))
+    payloads = [(enc, cut) for cut in list(range(0, 12)) + [r // 7, r // 3, r - 9, r - 5, r - 4, r - 2, r - 1]]
+    for k in range(24):   # garbage of a few bytes, decoded far past its end
+        g = np.zeros(64, np.uint8)
+        m = int(rng.integers(1, 40))
+        g[:m] = rng.integers(0, 256, m, dtype=np.uint8) if k % 3 else np.full(m, 255 * (k % 2), np.uint8)
+        payloads.append((g, m))
+    for buf, insize in payloads:
+        want = np.zeros(n + 8, np.uint8)
+        got = np.zeros(n + 8, np.uint8)
+        O.orc_cm_decode(refs.ptr(buf), insize, refs.ptr(want), n)
+        if refs.have_ref():   # the oracle itself is pinned on the reference for these payloads
+            pin = np.zeros(n + 8, np.uint8)
+            refs.ref_stages().ref_cm_decode(refs.ptr(buf.copy()), insize, refs.ptr(pin), n)
+            assert bytes(pin[:n]) == bytes(want[:n]), insize
+        assert E.emu_cm_decode(refs.ptr(buf), insize, refs.ptr(got), n) == 0
+        assert bytes(got[:n]) == bytes(want[:n]), insize
+
+
 @pytest.mark.parametrize("schedule", [1, 2])
 def test_cm_kernels_other_schedules(schedule):
     """Same result when the fibers are scheduled in descending or pseudo-random order."""

@@ -167,6 +167,30 @@ def test_stage_cm(st, O, name, data):
         assert bytes(dg[:n]) == bytes(dw[:n]), (insize, first_diff(dg[:n], dw[:n]))
 
 
+def test_stage_cm_exhausted_streams(st, O):
+    """Payloads that end early or are garbage, decoded far past their end (read_in() feeds -1, src/libbz3.c:345):
+    the decoder's shortcuts must be off once the stream is exhausted.  Same cases as the emulator test."""
+    rng = np.random.default_rng(31337)
+    base = arr(synth.zipf_text(64 << 10, seed=7))
+    n = 20000
+    bw = np.zeros(n + 16, np.uint8)
+    O.orc_bwt(refs.ptr(base[:n].copy()), refs.ptr(bw), n)
+    enc = np.zeros(2 * n + 64, np.uint8)
+    r = O.orc_cm_encode(refs.ptr(bw), n, refs.ptr(enc))
+    payloads = [(enc, cut) for cut in list(range(0, 12)) + [r // 7, r // 3, r - 9, r - 5, r - 4, r - 2, r - 1]]
+    for k in range(40):
+        g = np.zeros(64, np.uint8)
+        m = int(rng.integers(1, 40))
+        g[:m] = rng.integers(0, 256, m, dtype=np.uint8) if k % 3 else np.full(m, 255 * (k % 2), np.uint8)
+        payloads.append((g, m))
+    for buf, insize in payloads:
+        dw = np.zeros(n + 8, np.uint8)
+        dg = np.zeros(n + 8, np.uint8)
+        O.orc_cm_decode(refs.ptr(buf), insize, refs.ptr(dw), n)
+        assert st.L.bz3_b200_stage_cm_decode(st.handle, refs.ptr(buf), insize, refs.ptr(dg), n) == 0
+        assert bytes(dg[:n]) == bytes(dw[:n]), (insize, first_diff(dg[:n], dw[:n]))
+
+
 # ---------------------------------------------------------------- whole blocks
 @pytest.mark.parametrize("name,data", CASES, ids=IDS)
 def test_block_roundtrip_vs_oracle(st, name, data):
