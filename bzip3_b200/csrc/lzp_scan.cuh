@@ -153,6 +153,11 @@ __global__ void __launch_bounds__(kLzpEngThreads, 1) lzp_commit_kernel(const u8*
         while (ip < limit && op < out_stop) {
             const s32 W = (limit - ip) < wcap ? (limit - ip) : wcap;
             const bool active = t < W;
+            // Behind a match the step is narrow (128 positions = 4 of the 32 warps).  The other warps only keep the barriers
+            // company: measured with ncu on a source block, the block executed 34 warp instructions per input position, most
+            // of them in warps without a single active lane (profiles/r02_call28_ncu_lzp_commit_source16.md).
+            const bool wact = (s32)(warp * 32u) < W;
+            const int nwact = (W + 31) >> 5;
             const s32 p = ip + t;
             s32 val = 0;
             u32 c = 0, h = 0;
@@ -190,9 +195,12 @@ __global__ void __launch_bounds__(kLzpEngThreads, 1) lzp_commit_kernel(const u8*
                     c = (phase == 0 && val > 0) ? lzp_candidate_code(in, p, val, scan_end) : 0u;
                 }
             }
-            S.sval[t] = val;
-            S.scode[t] = (u8)c;
-            const u32 qb = __ballot_sync(kFullMask, c != 0u);
+            u32 qb = 0;
+            if (wact) {
+                S.sval[t] = val;
+                S.scode[t] = (u8)c;
+                qb = __ballot_sync(kFullMask, c != 0u);
+            }
             if (lane == 0) S.wmask[warp] = qb;
             if (t == 0) { S.match_lane = -1; S.match_len = 0; }
             __syncthreads();
@@ -231,12 +239,14 @@ __global__ void __launch_bounds__(kLzpEngThreads, 1) lzp_commit_kernel(const u8*
             const bool lit = t < nlit;
             const bool esc = lit && b == kLzpEscape && val > 0;   // :176-178, :181, :194
             const u32 cnt = lit ? (esc ? 2u : 1u) : 0u;
-            const u32 incl = warp_scan_incl(cnt);
-            if (lane == 31) S.wsum[warp] = incl;
+            u32 incl = 0;
+            if (wact) {
+                incl = warp_scan_incl(cnt);
+                if (lane == 31) S.wsum[warp] = incl;
+            }
             __syncthreads();
             u32 before = 0, total = 0;
-#pragma unroll
-            for (int k = 0; k < kLzpEngWarps; k++) {
+            for (int k = 0; k < nwact; k++) {   // uniform bound: the warps that hold positions of this step
                 const u32 v = S.wsum[k];
                 if ((u32)k < warp) before += v;
                 total += v;

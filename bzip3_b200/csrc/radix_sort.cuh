@@ -369,7 +369,11 @@ cudaError_t rs_histograms(cudaStream_t st, const K* keys, u32 n, int nbits, cons
     const u32 chunks = (n + kRsThreads * kRsHistItems - 1) / (kRsThreads * kRsHistItems);
     const u32 grid = chunks < 148u * 3u ? chunks : 148u * 3u;   // persistent: 3 blocks per SM (64 KiB of counters each)
     const size_t smem = rs_hist_smem(npass);
-    BZ_CUDA_TRY(cudaFuncSetAttribute(rs_hist_all_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // The limit is a property of the function on the device, shared by every host thread that codes a block on it: always
+    // the SAME value (the largest launch), never this launch's own size -- two threads with different pass counts would
+    // otherwise lower it under each other's launches ("too many resources requested for launch").
+    BZ_CUDA_TRY(cudaFuncSetAttribute(rs_hist_all_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)rs_hist_smem(kRsMaxPasses)));
     BZ_LAUNCH(grid, kRsThreads, smem, st, rs_hist_all_kernel<K>)(keys, n, nbits, T.ghist); BZ_NOTE_LAUNCH();
     BZ_LAUNCH(1, 32 * kRsMaxPasses, 0, st, rs_digit_scan_kernel)(T.ghist, npass); BZ_NOTE_LAUNCH();
     BZ_CUDA_TRY(cudaGetLastError());
@@ -387,7 +391,7 @@ cudaError_t rs_pass_sweep(cudaStream_t st, const K* kin, ValGen vgen, const u32*
     static const bool use_tma = !(getenv("BZ3_B200_RS_TMA") && getenv("BZ3_B200_RS_TMA")[0] == '0');   // A/B switch (tuning)
     auto kern = use_tma ? rs_onesweep_kernel<K, KOUT, VOUT, VTMA, true, ValGen> : rs_onesweep_kernel<K, KOUT, VOUT, VTMA, false, ValGen>;
     const size_t smem = rs_scatter_smem<K>();
-    // set every time: the attribute is per device and a process may drive several GPUs
+    // set every time (the attribute is per device and a process may drive several GPUs), always to the same value
     BZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BZ_LAUNCH(ntiles, kRsThreads, smem, st, kern)(kin, vgen, vin, kout, vout, n, shift, mask, T.ghist + 256 * pass_index, T.desc, T.ticket);
     BZ_NOTE_LAUNCH();

@@ -62,6 +62,38 @@ def test_batch_of_16mib_blocks_matches_reference():
             s.close()
 
 
+def test_many_blocks_of_mixed_sizes_at_once():
+    """40 states with different block sizes coded by 40 host threads at once, twice: sorts with different pass counts
+    (8 for the first round of a suffix sort, 2 * ceil(log2(n + 1)) / 8 afterwards, 3 for LZP, 1 for the inverse BWT) overlap
+    in time, so every per-function launch attribute must be the same for all of them.  (A histogram kernel whose shared
+    memory limit followed the launching thread's pass count failed here with "too many resources requested for launch".)"""
+    rng = np.random.default_rng(4040)
+    sizes = [int(x) for x in rng.integers(70 << 10, 3 << 20, 40)]
+    gens = [synth.zipf_text, synth.source_corpus, synth.log_stream]
+    datas = [gens[i % 3](n, seed=500 + i).tobytes()[:n] for i, n in enumerate(sizes)]
+    states = [bzip3_b200.Bz3State(max(len(d), 65 << 10)) for d in datas]
+    try:
+        for rep in range(2):
+            bufs = []
+            for d in datas:
+                b = np.zeros(bzip3_b200.bound(len(d)) + 64, np.uint8)
+                b[:len(d)] = np.frombuffer(d, np.uint8)
+                bufs.append(b)
+            enc = bzip3_b200.encode_blocks(states, bufs, [len(d) for d in datas])
+            assert all(s.last_error == 0 for s in states), [s.last_error for s in states]
+            assert all(e > 0 for e in enc), enc
+            if rep == 0:
+                for i in (0, 1, 2, 17, 39):
+                    want, r, _ = refs.oracle_encode_block(datas[i], max(len(datas[i]), 65 << 10))
+                    assert r == enc[i] and want == bytes(bufs[i][:enc[i]]), i
+            bzip3_b200.decode_blocks(states, bufs, [len(b) for b in bufs], enc, [len(d) for d in datas])
+            for d, b, s in zip(datas, bufs, states):
+                assert s.last_error == 0 and bytes(b[:len(d)]) == d
+    finally:
+        for s in states:
+            s.close()
+
+
 def _against_reference_big(n, data):
     """encode on the GPU and with the reference at the same time, compare, decode both ways"""
     import threading

@@ -387,6 +387,46 @@ __device__ __forceinline__ u32 walk_v8(const u32* pt, u32 code, u32 range_in, u3
     return pnode;
 }
 
+// V9: V7 with the row ADDRESS carried instead of the node: both children's row addresses are formed before the bit is known,
+// one select after it (instead of bit -> node -> address: three dependent instructions before the load can issue)
+__device__ __forceinline__ u32 walk_v9(const u32* pt, u32 code, u32 range_in, u32& range_out, u32& tmin_out) {
+    const u32 pbase = (u32)__cvta_generic_to_shared(pt);
+    uint4 g0, gk;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(g0.x), "=r"(g0.y), "=r"(g0.z), "=r"(g0.w) : "r"(pbase));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(gk.x), "=r"(gk.y), "=r"(gk.z), "=r"(gk.w) : "r"(pbase));
+    u32 ra = pbase + 16u, flow = 0, frange = range_in;   // ra = address of row(node) = pbase + 16 * node
+    u32 pcur = g0.y, kid0 = g0.z, kid1 = g0.w;
+    u32 x = mulhi_pinned(frange, pcur);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        u32 bit;
+        const u32 c0 = 2u * ra - pbase, c1 = c0 + 16u;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pb;\n\t"
+            ".reg .u32 mid, nx, r0;\n\t"
+            "add.u32 mid, %0, %2;\n\t"
+            "not.b32 nx, %2;\n\t"
+            "setp.le.u32 pb, %6, mid;\n\t"
+            "add.u32 r0, %1, nx;\n\t"
+            "selp.u32 %1, %2, r0, pb;\n\t"
+            "selp.u32 %3, %8, %7, pb;\n\t"
+            "selp.u32 %5, %10, %9, pb;\n\t"
+            "mul.hi.u32 %2, %1, %3;\n\t"
+            "@!pb add.u32 %0, mid, 1;\n\t"
+            "selp.u32 %4, 1, 0, pb;\n\t"
+            "}"
+            : "+r"(flow), "+r"(frange), "+r"(x), "+r"(pcur), "=r"(bit), "=r"(ra)
+            : "r"(code), "r"(kid0), "r"(kid1), "r"(c0), "r"(c1));
+        kid0 = bit ? gk.z : gk.x;
+        kid1 = bit ? gk.w : gk.y;
+        if (k < 5) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(gk.x), "=r"(gk.y), "=r"(gk.z), "=r"(gk.w) : "r"(ra));
+    }
+    tmin_out = flow ^ (flow + frange);
+    range_out = frange;
+    return (ra - pbase) >> 4;
+}
+
 template <int V>
 __global__ void k_walk(int nbytes, u32 seed, int slot) {
     __shared__ __align__(16) u32 ptab[512];
@@ -412,7 +452,8 @@ __global__ void k_walk(int nbytes, u32 seed, int slot) {
         else if (V == 5) node = walk_v5(pt, code, range, range, tm);
         else if (V == 6) node = walk_v6(pt, code, range, range, tm);
         else if (V == 7) node = walk_v7(pt, code, range, range, tm);
-        else node = walk_v8(pt, code, range, range, tm);
+        else if (V == 8) node = walk_v8(pt, code, range, range, tm);
+        else node = walk_v9(pt, code, range, range, tm);
         range |= 0xFF000000u;   // stands for the renormalisation: the range stays wide, the dependency stays
         if (tm < (1u << 24)) sum += 0x9E3779B9u;   // the tier test of the real kernel (here: rare or never)
         tacc = tm < tacc ? tm : tacc;
@@ -429,7 +470,7 @@ __global__ void k_walk(int nbytes, u32 seed, int slot) {
 
 int main() {
     const int n = 1 << 16;
-    const char* names[9] = {"V0 shipped fast tier (add, compare, 2 selects, 1 multiply)",
+    const char* names[10] = {"V0 shipped fast tier (add, compare, 2 selects, 1 multiply)",
                             "V1 compare d = code - low with x (no add before the compare)",
                             "V2 V1 + both next products before the bit is known",
                             "V3 V2 + rows of both children requested before the bit",
@@ -437,7 +478,8 @@ int main() {
                             "V5 V4 + rows of both children requested before the bit",
                             "V6 V1 with the borrow mask (one multiply, no predicate)",
                             "V7 V0 without the running minimum (one test per byte)",
-                            "V8 predicated exact walk (tier A), no shift ever due"};
+                            "V8 predicated exact walk (tier A), no shift ever due",
+                            "V9 V7 with the row address carried (one select between bit and load)"};
     for (int rep = 0; rep < 2; rep++) {
         k_walk<0><<<1, 32>>>(n, 777u, 0);
         k_walk<1><<<1, 32>>>(n, 777u, 1);
@@ -448,13 +490,14 @@ int main() {
         k_walk<6><<<1, 32>>>(n, 777u, 6);
         k_walk<7><<<1, 32>>>(n, 777u, 7);
         k_walk<8><<<1, 32>>>(n, 777u, 8);
+        k_walk<9><<<1, 32>>>(n, 777u, 9);
         cudaDeviceSynchronize();
     }
     u64 cyc[16];
     u32 sum[16];
     cudaMemcpyFromSymbol(cyc, g_cycles, sizeof(cyc));
     cudaMemcpyFromSymbol(sum, g_sum, sizeof(sum));
-    for (int v = 0; v < 9; v++)
+    for (int v = 0; v < 10; v++)
         printf("%-66s: %7.1f cycles per byte  (checksum %08x%s)\n", names[v], (double)cyc[v] / n, sum[v],
                sum[v] == sum[0] ? "" : "  MISMATCH");
     printf("status: %s\n", cudaGetErrorString(cudaGetLastError()));
