@@ -246,10 +246,19 @@ __global__ void __launch_bounds__(kLzpEngThreads, 1) lzp_commit_kernel(const u8*
             }
             __syncthreads();
             u32 before = 0, total = 0;
-            for (int k = 0; k < nwact; k++) {   // uniform bound: the warps that hold positions of this step
-                const u32 v = S.wsum[k];
-                if ((u32)k < warp) before += v;
-                total += v;
+            if (nwact == kLzpEngWarps) {   // full step (text without matches): unrolled
+#pragma unroll
+                for (int k = 0; k < kLzpEngWarps; k++) {
+                    const u32 v = S.wsum[k];
+                    if ((u32)k < warp) before += v;
+                    total += v;
+                }
+            } else {
+                for (int k = 0; k < nwact; k++) {   // uniform bound: the warps that hold positions of this step
+                    const u32 v = S.wsum[k];
+                    if ((u32)k < warp) before += v;
+                    total += v;
+                }
             }
             if (lit) {
                 const s32 o = op + (s32)(before + incl - cnt);

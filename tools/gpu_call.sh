@@ -1,9 +1,13 @@
 set -u
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests -m gpu -x -q --durations=5 ) > gpurun_out/r3d_pytest_gpu.log 2>&1
-echo "pytest rc $?"; tail -12 gpurun_out/r3d_pytest_gpu.log
-timeout 300 python tools/inflight_curve.py --mib 4 --ks 1,6,37,74,128,148,296 --out gpurun_out/r3d_inflight_zipf4m.json > gpurun_out/r3d_inflight_zipf4m.log 2>&1; tail -12 gpurun_out/r3d_inflight_zipf4m.log
-( time timeout 1500 python bench.py --steps 3 --warmup 3 ) > gpurun_out/r3d_bench.json 2> gpurun_out/r3d_bench.err
-echo "bench rc $?"; tail -c 400 gpurun_out/r3d_bench.json; tail -4 gpurun_out/r3d_bench.err
-( time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/r3d_bench_ref.json 2> gpurun_out/r3d_bench_ref.err
-echo "ref rc $?"; tail -c 300 gpurun_out/r3d_bench_ref.json
+L=gpurun_out/r3f_ab.log; : > $L
+( timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_stream.py -x -q 2>&1 | tail -3 ) | tee -a $L
+for c in zipf_text source_corpus; do
+  echo "== decoder, row address carried in the fast tier $c" >> $L
+  timeout 120 python tools/stage_driver.py cm_dec_bwt 4 2 $c 2>&1 | tail -1 >> $L
+  echo "== decoder, previous build $c" >> $L
+  BZ3_B200_LIB=tools/variants/lib_prev.so timeout 120 python tools/stage_driver.py cm_dec_bwt 4 2 $c 2>&1 | tail -1 >> $L
+done
+echo "== lzp 64 MiB zipf_text: unrolled warp-sum when all warps are active" >> $L
+timeout 200 python tools/stage_driver.py lzp 64 2 zipf_text 2>&1 | tail -1 >> $L
+cat $L
