@@ -49,7 +49,9 @@ def build_tools() -> None:
     os.makedirs(out, exist_ok=True)
     for cmd in ([NVCC] + FLAGS + ["-DBZ_CM_PROFILE", "-o", os.path.join(out, "lib_cmprof.so"), os.path.join(CSRC, "bz3_api.cu")],
                 [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", os.path.join(out, "ubench"),
-                 os.path.join(root, "tools", "ubench.cu")]):
+                 os.path.join(root, "tools", "ubench.cu")],
+                [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", os.path.join(out, "ubench_chain"),
+                 os.path.join(root, "tools", "ubench_chain.cu")]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
@@ -60,4 +62,4 @@ if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     if "--tools" in sys.argv:
         build_tools()
-        print("built tools/variants/lib_cmprof.so and tools/variants/ubench")
+        print("built tools/variants/lib_cmprof.so, tools/variants/ubench and tools/variants/ubench_chain")
