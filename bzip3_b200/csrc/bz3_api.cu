@@ -1095,7 +1095,9 @@ int stream_depth(int32_t block_size, int in_flight) {
         depth = sms;
     const size_t n = block_bound((size_t)block_size) + 64;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-        const size_t ws = 2 * std::max(sufsort_arena_bytes(n), other_arena_bytes(n)) + (size_t(1) << 30);
+        int slots = env_int("BZ3_B200_ARENAS", 2);   // the workspaces the states of this device will share (pool_attach)
+        slots = slots < 1 ? 1 : (slots > kMaxArenaSlots ? kMaxArenaSlots : slots);
+        const size_t ws = (size_t)slots * std::max(sufsort_arena_bytes(n), other_arena_bytes(n)) + (size_t(1) << 30);
         const size_t per_state = 3 * align_up(n + 256) + (size_t(2) << 20);
         depth = free_b > ws + per_state ? (int)std::min<size_t>((size_t)depth, (free_b - ws) / per_state) : 1;
     }

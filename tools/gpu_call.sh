@@ -1,13 +1,5 @@
 set -u
 mkdir -p gpurun_out
-L=gpurun_out/r3f_ab.log; : > $L
-( timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_stream.py -x -q 2>&1 | tail -3 ) | tee -a $L
-for c in zipf_text source_corpus; do
-  echo "== decoder, row address carried in the fast tier $c" >> $L
-  timeout 120 python tools/stage_driver.py cm_dec_bwt 4 2 $c 2>&1 | tail -1 >> $L
-  echo "== decoder, previous build $c" >> $L
-  BZ3_B200_LIB=tools/variants/lib_prev.so timeout 120 python tools/stage_driver.py cm_dec_bwt 4 2 $c 2>&1 | tail -1 >> $L
-done
-echo "== lzp 64 MiB zipf_text: unrolled warp-sum when all warps are active" >> $L
-timeout 200 python tools/stage_driver.py lzp 64 2 zipf_text 2>&1 | tail -1 >> $L
-cat $L
+L=gpurun_out/r3g_final_sanity.log; : > $L
+( timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -2 ) | tee -a $L
+( timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_large.py -x -q -k "not 511mib and not 256mib and not 64mib and not 32mib" 2>&1 | tail -3 ) | tee -a $L
