@@ -1,5 +1,3 @@
 set -u
 mkdir -p gpurun_out
-L=gpurun_out/r3g_final_sanity.log; : > $L
-( timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -2 ) | tee -a $L
-( timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_large.py -x -q -k "not 511mib and not 256mib and not 64mib and not 32mib" 2>&1 | tail -3 ) | tee -a $L
+BZ3_B200_ARENAS=4 timeout 45 python -m pytest tests/test_gpu_large.py -x -q -k "many_blocks or batch_of_16mib" 2>&1 | tail -3 | tee gpurun_out/r3h_arenas4.log
