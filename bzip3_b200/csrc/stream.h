@@ -72,6 +72,8 @@ struct Pipe {
     std::vector<Slot> slot;
     int result = 0;             // first error IN BLOCK ORDER (set by the writer), 0 while fine
     bool stop = false;          // set with it: the reader winds down
+    int states_live = 0;        // workers that own a state
+    int in_new = 0;             // workers inside bz3_new right now
     void fail(int code) {
         std::lock_guard<std::mutex> lk(m);
         if (!result) result = code;
@@ -92,26 +94,56 @@ inline int run(int in_fd, int out_fd, int32_t block_size, int in_flight, bool de
     P.slot.resize((size_t)in_flight);
     uint64_t n_in = 0, n_out = 0;
 
+    // A state is used by one block at a time: by its owner, or by a worker whose own bz3_new() failed (device memory
+    // tighter than the depth estimate: another process, a smaller GPU).  Such a worker borrows the state of a worker that
+    // has one instead of ending the stream with BZ3_ERR_INIT after part of the output has been written.
+    std::vector<std::mutex> state_mu((size_t)in_flight);
+
     auto worker = [&](int k) {
         Slot& S = P.slot[(size_t)k];
         if (thread_init) thread_init(worker_device[k]);   // block i is coded on the device of worker i mod in_flight
+        bool tried = false;
         for (;;) {
             {
                 std::unique_lock<std::mutex> lk(P.m);
                 P.cv.wait(lk, [&] { return S.phase == Slot::kFilled; });
                 if (S.last) return;
             }
-            if (!S.state) S.state = bz3_new(block_size);   // created on first use: a short file costs few states
-            if (!S.state) {
+            if (!S.state && !tried) {   // created on first use: a short file costs few states
+                tried = true;
+                { std::lock_guard<std::mutex> lk(P.m); P.in_new++; }
+                struct bz3_state* fresh = bz3_new(block_size);
+                {
+                    std::lock_guard<std::mutex> lk(P.m);
+                    S.state = fresh;
+                    P.in_new--;
+                    if (fresh) P.states_live++;
+                }
+                P.cv.notify_all();
+            }
+            struct bz3_state* st = nullptr;
+            int owner = k;
+            {
+                std::unique_lock<std::mutex> lk(P.m);
+                if (!S.state) P.cv.wait(lk, [&] { return P.states_live > 0 || P.in_new == 0; });   // somebody may still be getting one
+                for (int t = 0; t < in_flight && !st; t++) {
+                    const int j = (k + t) % in_flight;
+                    if (P.slot[(size_t)j].state) { st = P.slot[(size_t)j].state; owner = j; }
+                }
+            }
+            if (!st) {
                 S.out_size = -1;
                 S.error = BZ3_ERR_INIT;
-            } else if (!decode) {
-                S.out_size = bz3_encode_block(S.state, S.buf, S.in_size);
-                S.error = S.out_size < 0 ? bz3_last_error(S.state) : 0;
             } else {
-                S.out_size = bz3_decode_block(S.state, S.buf, cap, S.in_size, S.orig_size);
-                S.error = S.out_size < 0 ? bz3_last_error(S.state) : 0;
-                if (S.out_size < 0 && S.error == 0) S.error = BZ3_ERR_INIT;
+                std::lock_guard<std::mutex> use(state_mu[(size_t)owner]);
+                if (!decode) {
+                    S.out_size = bz3_encode_block(st, S.buf, S.in_size);
+                    S.error = S.out_size < 0 ? bz3_last_error(st) : 0;
+                } else {
+                    S.out_size = bz3_decode_block(st, S.buf, cap, S.in_size, S.orig_size);
+                    S.error = S.out_size < 0 ? bz3_last_error(st) : 0;
+                    if (S.out_size < 0 && S.error == 0) S.error = BZ3_ERR_INIT;
+                }
             }
             {
                 std::lock_guard<std::mutex> lk(P.m);

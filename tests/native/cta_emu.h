@@ -38,6 +38,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 
 // ThreadSanitizer build (tools/emu_tsan.py): every CUDA thread is announced to TSan as a fiber and every barrier /
 // warp collective as a release-acquire edge, so a shared- or global-memory access pair of two CUDA threads with no
@@ -491,12 +492,31 @@ template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 // memory, devices, streams, events: one "device", everything synchronous
 constexpr unsigned cudaStreamNonBlocking = 1;
+// test hook BZ_EMU_MALLOC_TOTAL: a "device" with that many bytes in all (live allocations are tracked)
+struct EmuDeviceHeap {
+    std::mutex m;
+    std::unordered_map<void*, size_t> live;
+    size_t used = 0;
+    static EmuDeviceHeap& get() { static EmuDeviceHeap h; return h; }
+};
 template <class T>
 inline cudaError_t cudaMalloc(T** p, size_t n) {
     if (const char* cap = getenv("BZ_EMU_MALLOC_MAX"))   // test hook: a "device" that cannot serve larger requests
         if (n > strtoull(cap, nullptr, 10)) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    const char* total = getenv("BZ_EMU_MALLOC_TOTAL");
+    if (total) {
+        EmuDeviceHeap& H = EmuDeviceHeap::get();
+        std::lock_guard<std::mutex> lk(H.m);
+        if (H.used + n > strtoull(total, nullptr, 10)) { *p = nullptr; return cudaErrorMemoryAllocation; }
+        H.used += n;
+    }
     *p = static_cast<T*>(aligned_alloc(256, (n + 255) & ~(size_t)255));
     if (*p) memset(*p, 0xCD, n);   // device memory is not zeroed
+    if (total && *p) {
+        EmuDeviceHeap& H = EmuDeviceHeap::get();
+        std::lock_guard<std::mutex> lk(H.m);
+        H.live[(void*)*p] = n;
+    }
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 template <class T>
@@ -504,7 +524,16 @@ inline cudaError_t cudaMallocHost(T** p, size_t n) {
     *p = static_cast<T*>(aligned_alloc(256, (n + 255) & ~(size_t)255));
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
-inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) {
+    if (p && getenv("BZ_EMU_MALLOC_TOTAL")) {
+        EmuDeviceHeap& H = EmuDeviceHeap::get();
+        std::lock_guard<std::mutex> lk(H.m);
+        auto it = H.live.find(p);
+        if (it != H.live.end()) { H.used -= it->second; H.live.erase(it); }
+    }
+    free(p);
+    return cudaSuccess;
+}
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }

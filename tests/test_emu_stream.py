@@ -325,3 +325,34 @@ def test_mutated_containers_follow_the_reference_loop(L, tmp_path):
         rc, back, _, _ = decode_bytes(L, tmp_path, blob, 1 + trial % 3, name="m%d" % trial)
         assert rc == want[0], (trial, kind, rc, want[0])
         assert back == want[1], (trial, kind, len(back), len(want[1]))
+
+
+def test_workers_without_a_state_borrow_one(tmp_path):
+    """Device memory for two states, six workers: the four whose bz3_new() fails code their blocks on a state of the other
+    two (one block at a time per state) instead of ending the stream with BZ3_ERR_INIT after part of the output is written.
+    A device with no room for any state still reports BZ3_ERR_INIT.  Runs in a subprocess: the memory cap of the emulated
+    device (BZ_EMU_MALLOC_TOTAL) is read from the environment."""
+    import sys
+    so = build_emulated_library()
+    data = squeezable(11 * BS + 1234, seed=91)
+    (tmp_path / "in.bin").write_bytes(data)
+    (tmp_path / "want.bz3").write_bytes(container(data, BS))
+    script = (
+        "import ctypes as C, os, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import bzip3_b200\n"
+        "L = bzip3_b200.lib()\n"
+        "d = %r\n"
+        "fi = os.open(d + '/in.bin', os.O_RDONLY); fo = os.open(d + '/out.bz3', os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)\n"
+        "nin, nout = C.c_uint64(0), C.c_uint64(0)\n"
+        "rc = L.bz3_b200_encode_fd(fi, fo, %d, 6, C.byref(nin), C.byref(nout)); os.close(fi); os.close(fo)\n"
+        "print('ENC', rc, open(d + '/out.bz3', 'rb').read() == open(d + '/want.bz3', 'rb').read())\n"
+        "fi = os.open(d + '/want.bz3', os.O_RDONLY); fo = os.open(d + '/back.bin', os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)\n"
+        "rc = L.bz3_b200_decode_fd(fi, fo, 6, C.byref(nin), C.byref(nout)); os.close(fi); os.close(fo)\n"
+        "print('DEC', rc, open(d + '/back.bin', 'rb').read() == open(d + '/in.bin', 'rb').read())\n" % (refs.ROOT, str(tmp_path), BS))
+    own = 3.2 * bzip3_b200.bound(BS) + (1 << 20) + 8192        # what a state owns (test_emu_library)
+    for total, want in ((int(2 * 52 * BS + 2.5 * own), ("ENC 0 True", "DEC 0 True")),      # two workspaces + two states
+                        (int(0.5 * own), ("ENC %d False" % bzip3_b200.BZ3_ERR_INIT, "DEC %d False" % bzip3_b200.BZ3_ERR_INIT))):
+        env = dict(os.environ, BZ3_B200_LIB=so, BZ_EMU_MALLOC_TOTAL=str(total))
+        out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900)
+        assert all(w in out.stdout for w in want), (total, out.stdout, out.stderr[-2000:])

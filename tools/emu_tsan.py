@@ -10,8 +10,9 @@ another here), memory-ordering subtleties below the barrier level.
 
     python tools/emu_tsan.py          (re-executes itself with libtsan preloaded; takes a few minutes)
 
-Expected output: one line per kernel, "no race reported" -- except the two tree-decoder kernels whose chain warp
-stores the decoded byte from all 32 lanes at once (the same value to the same address: reported, benign by design)."""
+Expected output: one line per job, "no race reported" -- except cm_decode_kernel, whose chain warp stores the decoded byte
+from all 32 lanes at once (the same value to the same address, twice per byte: "2 x bz3::cm_decode_kernel", benign by
+design; every job that decodes shows it)."""
 import ctypes as C
 import os
 import re
@@ -92,8 +93,8 @@ def child(kind, variant):
             back = np.zeros(n + 8, np.uint8)
             L.emu_cm_decode(refs.ptr(want), rw, refs.ptr(back), n)
             ok = bytes(back[:n]) == bytes(data)
-    elif kind == "lzp":
-        L = C.CDLL(KSO)
+    elif kind == "lzp":   # encoder: scan kernels + in-order commit engine (emu_stages); decoder: one thread block (emu_check)
+        L, S2 = C.CDLL(KSO), C.CDLL(SSO)
         src = synth.log_stream(5000, seed=3)
         m = len(src)
         pad = np.zeros(m + 64, np.uint8)
@@ -102,14 +103,15 @@ def child(kind, variant):
         lp = lut.ctypes.data_as(refs.i32p)
         lw = np.zeros(m + 64, np.uint8)
         r0 = O.orc_lzp_encode(refs.ptr(pad), m, refs.ptr(lw), lp)
-        enc, dec = L.emu_lzp_encode, L.emu_lzp_decode
+        enc, dec = S2.emu_stage_lzp_encode, L.emu_lzp_decode
         for f in (enc, dec):
             f.restype = C.c_int32
-        enc.argtypes = [u8p, C.c_int32, u8p, refs.i32p]
+        enc.argtypes = [u8p, C.c_int32, u8p]
         dec.argtypes = [u8p, C.c_int32, u8p, C.c_int32, refs.i32p]
         lg = np.zeros(m + 64, np.uint8)
-        ok = enc(refs.ptr(pad), m, refs.ptr(lg), lp) == r0 and bytes(lg[:r0]) == bytes(lw[:r0])
+        ok = enc(refs.ptr(pad), m, refs.ptr(lg)) == r0 and bytes(lg[:r0]) == bytes(lw[:r0])
         d = np.zeros(refs.bound(m) + 64, np.uint8)
+        lut[:] = 0
         ok = ok and dec(refs.ptr(lw), r0, refs.ptr(d), refs.bound(m), lp) == m and bytes(d[:m]) == bytes(src)
     else:  # the multi-kernel stages
         L = C.CDLL(SSO)
@@ -148,7 +150,7 @@ def main():
                                         "-lpthread"])
     tsan = subprocess.check_output(["g++", "-print-file-name=libtsan.so"], text=True).strip()
     env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
-    jobs = [("enc", v) for v in (0, 2, 4, 6)] + [("dec", v) for v in (0, 3, 4, 5, 6, 7, 8, 9)] + [("lzp", 0), ("lzp", 2), ("stages", 0), ("lib", 1), ("lib", 2), ("stream", 3)]
+    jobs = [("enc", 0), ("dec", 0), ("lzp", 0), ("stages", 0), ("lib", 1), ("lib", 2), ("lib", 4), ("stream", 3)]
     only = os.environ.get("EMU_TSAN_ONLY")   # e.g. EMU_TSAN_ONLY=lib,stages
     jobs = [j for j in jobs if not only or j[0] in only.split(",")]
     bad = 0
@@ -165,7 +167,7 @@ def main():
             fr = re.findall(r"#0 (?:void )?([\w:<>, ]+?)\(", blk)
             key = " <-> ".join(sorted(set(f.strip() for f in fr[:2])))
             races[key] = races.get(key, 0) + 1
-        name = {"enc": "CM encoder", "dec": "CM decoder", "lzp": "LZP encoder+decoder variant", "stages": "CRC / mRLE / BWT / inverse BWT",
+        name = {"enc": "CM encoder", "dec": "CM decoder", "lzp": "LZP encoder + decoder", "stages": "CRC / mRLE / BWT / inverse BWT",
                 "lib": "library, 4-block batch, workspaces", "stream": "container front end, 3 blocks, workers"}[kind]
         line = "%-30s %d: %s, " % (name, v, result)
         line += "no race reported" if not races else "; ".join("%d x %s" % (c, k) for k, c in races.items())
